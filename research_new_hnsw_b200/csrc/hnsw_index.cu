@@ -1,0 +1,306 @@
+// hnsw_index.cu -- HBM image management and search dispatch for HnswIndex.
+#include <algorithm>
+#include <cstdlib>
+
+#include "hnsw_index.cuh"
+
+namespace b200 {
+
+HnswIndex::~HnswIndex() {
+    if (dev.cap || dev.err_flag) {
+        cudaSetDevice(dev.device);
+        dev.release();
+    }
+    cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int HnswIndex::init_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+        return B200HNSW_E_CUDA;
+    }
+    int d = prm.device;
+    if (d < 0) B200_CUDA_OK(cudaGetDevice(&d));
+    if (d >= count) {
+        set_error("device ordinal out of range");
+        return B200HNSW_E_ARG;
+    }
+    dev.device = d;
+    B200_CUDA_OK(cudaSetDevice(d));
+    B200_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_CUDA_OK(cudaEventCreate(&ev0));
+    B200_CUDA_OK(cudaEventCreate(&ev1));
+    return 0;
+}
+
+int HnswIndex::alloc_device(size_t cap) {
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    dev.release();
+    dev.cap = cap;
+    dev.dim = host.dim;
+    dev.d4 = (host.dim + 3) / 4;
+    dev.maxM = host.maxM;
+    dev.maxM0 = host.maxM0;
+    const size_t c = cap ? cap : 1;
+    B200_CUDA_OK(cudaMalloc(&dev.vec, c * dev.d4 * 16));
+    B200_CUDA_OK(cudaMalloc(&dev.links0, c * dev.maxM0 * 4));
+    B200_CUDA_OK(cudaMalloc(&dev.up_base, c * 4));
+    B200_CUDA_OK(cudaMalloc(&dev.labels, c * 8));
+    B200_CUDA_OK(cudaMalloc(&dev.err_flag, 4));
+    B200_CUDA_OK(cudaMemset(dev.err_flag, 0, 4));
+    B200_CUDA_OK(cudaMemset(dev.up_base, 0xFF, c * 4));
+    B200_CUDA_OK(cudaMemset(dev.links0, 0xFF, c * dev.maxM0 * 4));
+    return 0;
+}
+
+int HnswIndex::upload_upper() {
+    const size_t n = host.cur;
+    std::vector<uint32_t> base(n ? n : 1, kEmpty);
+    size_t lists = 0;
+    for (size_t i = 0; i < n; i++)
+        if (host.levels[i] > 0) {
+            base[i] = (uint32_t)lists;
+            lists += (size_t)host.levels[i];
+        }
+    std::vector<uint32_t> up((lists ? lists : 1) * host.maxM, kEmpty);
+    for (size_t i = 0; i < n; i++) {
+        for (int l = 1; l <= host.levels[i]; l++) {
+            const uint32_t *ll = host.list(i, l);
+            const unsigned cnt = HostImage::count_of(ll);
+            if (cnt > host.maxM) {
+                set_error("Index seems to be corrupted or unsupported");
+                return B200HNSW_E_CORRUPT;
+            }
+            uint32_t *dst = up.data() + ((size_t)base[i] + (l - 1)) * host.maxM;
+            for (unsigned j = 0; j < cnt; j++) {
+                const uint32_t v = ll[1 + j];
+                // a neighbour on level l must itself own a level-l list (hnswalg.h:547-548)
+                if (v >= n || host.levels[v] < l) {
+                    set_error("cand error");
+                    return B200HNSW_E_CAND;
+                }
+                dst[j] = v;
+            }
+        }
+    }
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    if (lists > dev.up_lists_cap || !dev.links_up) {
+        cudaFree(dev.links_up);
+        dev.links_up = nullptr;
+        dev.up_lists_cap = std::max<size_t>(lists, 1);
+        B200_CUDA_OK(cudaMalloc(&dev.links_up, dev.up_lists_cap * host.maxM * 4));
+    }
+    dev.up_lists = lists;
+    B200_CUDA_OK(cudaMemcpy(dev.links_up, up.data(), std::max<size_t>(lists, 1) * host.maxM * 4, cudaMemcpyHostToDevice));
+    if (n) B200_CUDA_OK(cudaMemcpy(dev.up_base, base.data(), n * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int HnswIndex::upload_all() {
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    const size_t n = host.cur;
+    dev.n = n;
+    if (n) {
+        // stream the raw level-0 block through a bounded staging buffer and de-interleave it on the device
+        const size_t rec = host.size_data;
+        const size_t chunk = std::max<size_t>(1, std::min<size_t>(n, (size_t)(256u << 20) / rec));
+        uint32_t *raw = nullptr;
+        B200_CUDA_OK(cudaMalloc(&raw, chunk * rec));
+        for (size_t first = 0; first < n; first += chunk) {
+            const size_t cnt = std::min(chunk, n - first);
+            cudaError_t e = cudaMemcpy(raw, host.level0 + first * rec, cnt * rec, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                const unsigned threads = 256;
+                const unsigned blocks = (unsigned)((cnt * 32 + threads - 1) / threads);
+                deinterleave_kernel<<<blocks, threads>>>(raw, rec / 4, (uint32_t)first, (uint32_t)cnt,
+                                                         (uint32_t)host.maxM0, (uint32_t)host.dim, (uint32_t)dev.d4,
+                                                         (uint32_t)n, (float *)dev.vec, dev.links0, dev.labels,
+                                                         dev.err_flag);
+                e = cudaDeviceSynchronize();
+            }
+            if (e != cudaSuccess) {
+                cudaFree(raw);
+                set_error(std::string("CUDA error during upload: ") + cudaGetErrorString(e));
+                return B200HNSW_E_CUDA;
+            }
+        }
+        cudaFree(raw);
+        uint32_t flag = 0;
+        B200_CUDA_OK(cudaMemcpy(&flag, dev.err_flag, 4, cudaMemcpyDeviceToHost));
+        if (flag) {
+            set_error(flag & 2 ? "Index seems to be corrupted or unsupported" : "cand error");
+            return flag & 2 ? B200HNSW_E_CORRUPT : B200HNSW_E_CAND;
+        }
+    }
+    linked = n;
+    return upload_upper();
+}
+
+int HnswIndex::ensure_scratch(size_t nq, size_t k) {
+    if (nq <= scratch_q && k <= scratch_k) return 0;
+    const size_t q = std::max(nq, scratch_q), kk = std::max(k, scratch_k);
+    cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
+    dQ = nullptr; dLabels = nullptr; dDists = nullptr; dCounts = dWork = nullptr;
+    scratch_q = scratch_k = 0;
+    B200_CUDA_OK(cudaMalloc(&dQ, q * host.dim * 4));
+    B200_CUDA_OK(cudaMalloc(&dLabels, q * kk * 8));
+    B200_CUDA_OK(cudaMalloc(&dDists, q * kk * 4));
+    B200_CUDA_OK(cudaMalloc(&dCounts, q * 4));
+    B200_CUDA_OK(cudaMalloc(&dWork, q * 16));
+    scratch_q = q;
+    scratch_k = kk;
+    return 0;
+}
+
+// Visited-table size: large enough that a typical query at this ef never rebuilds it (D ~ 30*ef + 500 on the
+// 1M x 128, M=32 graph), bounded so several CTAs still fit in an SM's 228 KB.
+uint32_t pick_hash_bits(size_t ef, size_t list_cap) {
+    if (const char *e = getenv("B200HNSW_HASH_BITS")) {
+        const int b = atoi(e);
+        if (b >= 8 && b <= 15) {
+            size_t need = 2 * (ef + list_cap);
+            uint32_t bits = (uint32_t)b;
+            while ((1ull << bits) < need) bits++;
+            return bits;
+        }
+    }
+    size_t want = 64 * ef + 1024;
+    if (want > 16384) want = 16384;
+    const size_t need = 2 * (ef + list_cap);
+    if (want < need) want = need;
+    uint32_t bits = 10;
+    while ((1ull << bits) < want) bits++;
+    return bits;
+}
+
+template <int LPV, int CPL, int METRIC>
+static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
+    static bool configured[16] = {};  // per device; set once (benign race: idempotent)
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 16 && !configured[d]) {
+        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<LPV, CPL, METRIC>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured[d] = true;
+    }
+    hnsw_search_kernel<LPV, CPL, METRIC><<<a.nq, kTeam, smem, st>>>(a);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int METRIC>
+static int launch_metric(const SearchArgs &a, size_t smem, cudaStream_t st) {
+    const uint32_t d4 = a.d4;
+    if (d4 <= 8) return launch_one<8, 1, METRIC>(a, smem, st);
+    if (d4 <= 16) return launch_one<8, 2, METRIC>(a, smem, st);
+    if (d4 <= 24) return launch_one<8, 3, METRIC>(a, smem, st);
+    if (d4 <= 32) return launch_one<8, 4, METRIC>(a, smem, st);
+    if (d4 <= 48) return launch_one<16, 3, METRIC>(a, smem, st);
+    if (d4 <= 64) return launch_one<16, 4, METRIC>(a, smem, st);
+    if (d4 <= 96) return launch_one<32, 3, METRIC>(a, smem, st);
+    if (d4 <= 128) return launch_one<32, 4, METRIC>(a, smem, st);
+    if (d4 <= 192) return launch_one<32, 6, METRIC>(a, smem, st);
+    if (d4 <= 256) return launch_one<32, 8, METRIC>(a, smem, st);
+    set_error("dimension > 1024 is not supported by the search kernel");
+    return B200HNSW_E_UNSUPPORTED;
+}
+
+int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd,
+                             uint32_t *dc, uint32_t *dw, cudaStream_t st) {
+    if (nq == 0) return 0;
+    if (k == 0 || !dQ_ || !dl || !dd) {
+        set_error("search: null pointer or k == 0");
+        return B200HNSW_E_ARG;
+    }
+    if (host.num_deleted) {
+        set_error("search with deleted elements (non-bare-bone path, hnswalg.h:406-407) is not supported yet");
+        return B200HNSW_E_UNSUPPORTED;
+    }
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    if (host.cur == 0) {  // hnswalg.h:1273: empty index -> empty result
+        B200_CUDA_OK(cudaMemsetAsync(dl, 0xFF, nq * k * 8, st));
+        fill_pad_rows(dd, dc, dw, nq, k, st);  // dist = +inf, counts = 0
+        return 0;
+    }
+    size_t efx = ef_ ? ef_ : ef;
+    efx = std::max(efx, k);  // hnswalg.h:1309
+    if (efx > 4096) {
+        set_error("ef > 4096 is not supported");
+        return B200HNSW_E_UNSUPPORTED;
+    }
+    const size_t list_cap = std::max(host.maxM, host.maxM0);
+    SearchArgs a{};
+    a.vec = dev.vec; a.links0 = dev.links0; a.up_base = dev.up_base; a.links_up = dev.links_up;
+    a.labels = dev.labels; a.Q = dQ_; a.out_labels = dl; a.out_dists = dd; a.out_counts = dc; a.out_work = dw;
+    a.n = (uint32_t)linked; a.entry = host.enterpoint; a.maxlevel = host.maxlevel;
+    a.dim = (uint32_t)host.dim; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)host.maxM; a.maxM0 = (uint32_t)host.maxM0;
+    a.nq = (uint32_t)nq; a.k = (uint32_t)k; a.ef = (uint32_t)efx;
+    a.hash_bits = pick_hash_bits(efx, list_cap);
+    const SearchSmem L(a.ef, (uint32_t)list_cap, a.d4, a.hash_bits);
+    if (L.total > 227 * 1024) {
+        set_error("search configuration needs more than 227 KB of shared memory");
+        return B200HNSW_E_UNSUPPORTED;
+    }
+    stats.kernel_launches += 1;
+    return prm.metric == B200HNSW_L2 ? launch_metric<0>(a, L.total, st) : launch_metric<1>(a, L.total, st);
+}
+
+__global__ void fill_pad_kernel(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq * k) dd[i] = __int_as_float(0x7f800000);
+    if (dc && i < nq) dc[i] = 0;
+    if (dw && i < nq * 4) dw[i] = 0;
+}
+
+void fill_pad_rows(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k, cudaStream_t st) {
+    const size_t tot = std::max(nq * k, nq * 4);
+    fill_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dd, dc, dw, nq, k);
+}
+
+int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
+                           uint32_t *counts, uint32_t *work) {
+    if (nq == 0) return 0;
+    if (!Q || !labels || !dists || k == 0) {
+        set_error("search: null pointer or k == 0");
+        return B200HNSW_E_ARG;
+    }
+    std::lock_guard<std::mutex> g(mu);
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    int rc = ensure_scratch(nq, k);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaMemcpyAsync(dQ, Q, nq * host.dim * 4, cudaMemcpyHostToDevice, stream));
+    B200_CUDA_OK(cudaEventRecord(ev0, stream));
+    rc = launch_search(dQ, nq, k, ef_, dLabels, dDists, dCounts, dWork, stream);
+    if (rc) return rc;
+    B200_CUDA_OK(cudaEventRecord(ev1, stream));
+    B200_CUDA_OK(cudaMemcpyAsync(labels, dLabels, nq * k * 8, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_OK(cudaMemcpyAsync(dists, dDists, nq * k * 4, cudaMemcpyDeviceToHost, stream));
+    if (counts) B200_CUDA_OK(cudaMemcpyAsync(counts, dCounts, nq * 4, cudaMemcpyDeviceToHost, stream));
+    std::vector<uint32_t> wtmp;
+    uint32_t *w = work;
+    if (!w) {
+        wtmp.resize(nq * 4);
+        w = wtmp.data();
+    }
+    B200_CUDA_OK(cudaMemcpyAsync(w, dWork, nq * 16, cudaMemcpyDeviceToHost, stream));
+    B200_CUDA_OK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    stats.last_kernel_ms = ms;
+    stats.queries = nq;
+    stats.dist_evals = stats.hops_base = stats.hops_upper = stats.visited_resets = 0;
+    for (size_t i = 0; i < nq; i++) {
+        stats.dist_evals += w[i * 4 + 0];
+        stats.hops_base += w[i * 4 + 1];
+        stats.hops_upper += w[i * 4 + 2];
+        stats.visited_resets += w[i * 4 + 3];
+    }
+    return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,47 @@
+// hnsw_index.cuh -- HierarchicalNSW<float> replacement: host mirror + HBM image + kernel dispatch.
+#pragma once
+#include <mutex>
+#include <vector>
+
+#include "device_index.cuh"
+#include "search_kernel.cuh"
+
+namespace b200 {
+
+struct HnswIndex {
+    b200hnsw_params prm{};
+    HostImage host;
+    DeviceIndex dev;
+    size_t ef = 10;  // hnswalg.h:115
+    std::mutex mu;   // serialises host-pointer calls that share the scratch buffers
+    b200hnsw_stats stats{};
+    // staged insertions (add_batch before flush): ids [linked, host.cur) are not yet in the graph
+    size_t linked = 0;
+    // scratch for the host-pointer search path
+    float *dQ = nullptr;
+    uint64_t *dLabels = nullptr;
+    float *dDists = nullptr;
+    uint32_t *dCounts = nullptr, *dWork = nullptr;
+    size_t scratch_q = 0, scratch_k = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    ~HnswIndex();
+    int init_device();
+    int alloc_device(size_t cap);
+    int upload_all();                       // host mirror -> HBM (after load)
+    int upload_upper();                     // rebuild up_base / links_up from the host mirror
+    int ensure_scratch(size_t nq, size_t k);
+    int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
+                      uint32_t *dw, cudaStream_t st);
+    int search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
+                    uint32_t *counts, uint32_t *work);
+    // build.cu: addPoint staging and the batched GPU graph build
+    int add_batch(const float *X, const uint64_t *labels, size_t n);
+    int flush();
+};
+
+uint32_t pick_hash_bits(size_t ef, size_t list_cap);
+void fill_pad_rows(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k, cudaStream_t st);
+
+}  // namespace b200

@@ -1,0 +1,390 @@
+// search_kernel.cuh -- batched HNSW searchKnn on sm_100a: one 128-thread CTA per query.
+//
+// Replaces, for a whole batch of queries per launch (all file:line under /root/reference/hnswlib):
+//   hnswalg.h:1270-1324  searchKnn            -> prologue (upper-layer greedy descent) + epilogue (top-k, labels)
+//   hnswalg.h:309-440    searchBaseLayerST<bare_bone_search=true> -> the hop loop below
+//   visited_list_pool.h  VisitedList tags     -> per-query open-addressing hash in shared memory
+//   space_l2.h:97-143 / space_ip.h:255-303   -> sub-warp fp32 reductions (LPV lanes x 128-bit loads per vector)
+//
+// Equivalences used (each argued from the cited reference code):
+//  * In bare-bone mode a node enters candidate_set and top_candidates together (:398-408) and leaves
+//    top_candidates only as the current worst (:418-429); lowerBound never increases once the heap is full and
+//    the loop stops when the best unexpanded candidate is > lowerBound (:347-358).  The live frontier is
+//    therefore exactly the not-yet-expanded entries of the top-ef set: ONE sorted buffer of <= ef keys
+//    (dist, id, expanded-bit) replaces both std::priority_queues.
+//  * All unvisited neighbours of the expanded node are evaluated in parallel and filtered against the
+//    pre-expansion bound -- a superset of what the sequential loop admits (:395); extras fall off the end of the
+//    sorted buffer at the merge.  Same final buffer (up to exact float ties).
+//  * "visited" means "distance already evaluated" (:385-386).  When the hash exceeds half load it is rebuilt
+//    from the ids in the buffer; a forgotten node can only be re-evaluated and is then rejected by the bound
+//    (it was rejected or evicted at a bound >= the current one), so results do not change.
+//
+// Data layout (device_index.cuh): vec[N][d4] float4 rows (zero padded), links0[N][maxM0] u32 padded with kEmpty,
+// links_up[list][maxM] u32 padded with kEmpty, up_base[N] = index of the node's level-1 list or kEmpty.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kTeam = 128;  // threads per query
+
+struct SearchArgs {
+    const float4 *vec;        // [n][d4]
+    const uint32_t *links0;   // [n][maxM0]
+    const uint32_t *up_base;  // [n]
+    const uint32_t *links_up; // [lists][maxM]
+    const uint64_t *labels;   // [n]
+    const float *Q;           // [nq][dim]
+    uint64_t *out_labels;     // [nq][k]
+    float *out_dists;         // [nq][k]
+    uint32_t *out_counts;     // [nq] or null
+    uint32_t *out_work;       // [nq][4] or null: D, H0, Hup, resets
+    uint32_t n, entry;
+    int32_t maxlevel;
+    uint32_t dim, d4, maxM, maxM0;
+    uint32_t nq, k, ef;
+    uint32_t hash_bits;
+};
+
+// shared-memory carve-up, shared by host (size) and device (pointers)
+struct SearchSmem {
+    uint32_t off_buf0, off_buf1, off_acc, off_ids, off_dist, off_q, off_hash, total;
+    __host__ __device__ SearchSmem(uint32_t ef, uint32_t list_cap, uint32_t d4, uint32_t hash_bits) {
+        uint32_t o = 0;
+        off_buf0 = o; o += ef * 8;
+        off_buf1 = o; o += ef * 8;
+        off_acc = o;  o += list_cap * 8;
+        off_ids = o;  o += list_cap * 4;
+        off_dist = o; o += list_cap * 4;
+        o = (o + 15) & ~15u;
+        off_q = o;    o += d4 * 16;
+        off_hash = o; o += (1u << hash_bits) * 4;
+        total = o;
+    }
+};
+
+// Sum over the LPV lanes of a group.  Groups of one warp may run different trip counts, so the shuffle names only
+// the lanes of its own group.
+template <int LPV>
+__device__ __forceinline__ float group_sum(float v, uint32_t gmask) {
+#pragma unroll
+    for (int o = LPV / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+template <int METRIC>
+__device__ __forceinline__ float acc4(float acc, const float4 &q, const float4 &v) {
+    if (METRIC == 0) {
+        float a = q.x - v.x, b = q.y - v.y, c = q.z - v.z, d = q.w - v.w;
+        acc = fmaf(a, a, acc); acc = fmaf(b, b, acc); acc = fmaf(c, c, acc); acc = fmaf(d, d, acc);
+    } else {
+        acc = fmaf(q.x, v.x, acc); acc = fmaf(q.y, v.y, acc); acc = fmaf(q.z, v.z, acc); acc = fmaf(q.w, v.w, acc);
+    }
+    return acc;
+}
+
+// Distances from the query (register slices q[]) to ids[0..n): each group of LPV lanes owns one vector at a time,
+// two vectors (2*CPL 128-bit loads per lane) are in flight per group.  dists[j] is written by the group leader.
+template <int LPV, int CPL, int METRIC>
+__device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *__restrict__ vec, uint32_t d4,
+                                          const uint32_t *ids, int n, float *dists, int grp, int sub) {
+    constexpr int NGRP = kTeam / LPV;
+    const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
+    for (int j = grp; j < n; j += 2 * NGRP) {
+        const int j2 = j + NGRP;
+        const bool has2 = j2 < n;
+        const float4 *ra = vec + (size_t)ids[j] * d4;
+        const float4 *rb = vec + (size_t)ids[has2 ? j2 : j] * d4;
+        float4 va[CPL], vb[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = sub + c * LPV;
+            va[c] = idx < d4 ? ldg_stream(ra + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = sub + c * LPV;
+            vb[c] = (has2 && idx < d4) ? ldg_stream(rb + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = sub + c * LPV;
+            if (idx < d4) {
+                sa = acc4<METRIC>(sa, q[c], va[c]);
+                sb = acc4<METRIC>(sb, q[c], vb[c]);
+            }
+        }
+        sa = group_sum<LPV>(sa, gmask);
+        sb = group_sum<LPV>(sb, gmask);
+        if (METRIC == 1) { sa = 1.0f - sa; sb = 1.0f - sb; }
+        if (sub == 0) {
+            dists[j] = sa;
+            if (has2) dists[j2] = sb;
+        }
+    }
+}
+
+__device__ __forceinline__ bool hash_insert(uint32_t *tab, uint32_t bits, uint32_t id) {
+    const uint32_t mask = (1u << bits) - 1u;
+    uint32_t h = (id * 0x9E3779B1u) >> (32 - bits);
+    for (;;) {
+        const uint32_t old = atomicCAS(&tab[h], kEmpty, id);
+        if (old == kEmpty) return true;
+        if (old == id) return false;
+        h = (h + 1) & mask;
+    }
+}
+
+template <int LPV, int CPL, int METRIC>
+__global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
+    const SearchSmem L(p.ef, list_cap, p.d4, p.hash_bits);
+    uint64_t *const buf_a = (uint64_t *)(smem + L.off_buf0), *const buf_b = (uint64_t *)(smem + L.off_buf1);
+    uint64_t *acc = (uint64_t *)(smem + L.off_acc);
+    uint32_t *ids = (uint32_t *)(smem + L.off_ids);
+    float *dist = (float *)(smem + L.off_dist);
+    float *qs = (float *)(smem + L.off_q);
+    uint32_t *hash = (uint32_t *)(smem + L.off_hash);
+    __shared__ int s_cnt;        // entries in ids[] / acc[]
+    __shared__ int s_next;       // position of the first unexpanded buffer entry (>= size: none)
+    __shared__ int s_best;       // upper layers: argmin slot
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sub = tid % LPV, grp = tid / LPV;
+    const uint32_t qi = blockIdx.x;
+    const uint32_t ef = p.ef, d4 = p.d4;
+    const uint32_t HS = 1u << p.hash_bits;
+
+    // ---- stage the query (rows of Q are only 4-byte aligned when dim % 4 != 0) and clear the visited table ----
+    for (uint32_t i = tid; i < d4 * 4; i += kTeam) qs[i] = i < p.dim ? p.Q[(size_t)qi * p.dim + i] : 0.f;
+    for (uint32_t i = tid; i < HS; i += kTeam) hash[i] = kEmpty;
+    if (tid == 0) { s_cnt = 0; s_next = 0; }
+    __syncthreads();
+    float4 q[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+        const uint32_t idx = sub + c * LPV;
+        q[c] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    uint32_t wD = 0, wH0 = 0, wHup = 0, wReset = 0;  // work counters (meaningful in thread 0)
+
+    // ---- searchKnn prologue: distance to the entry point, greedy descent on levels maxlevel..1 ----
+    uint32_t cur = p.entry;
+    if (tid == 0) ids[0] = cur;
+    __syncthreads();
+    eval_list<LPV, CPL, METRIC>(q, p.vec, d4, ids, 1, dist, grp, sub);
+    __syncthreads();
+    float curdist = dist[0];
+    wD += 1;
+    for (int level = p.maxlevel; level > 0; --level) {
+        bool changed = true;
+        while (changed) {
+            changed = false;
+            __syncthreads();  // previous round's reads of ids/dist/s_best are done
+            const uint32_t base = __ldg(p.up_base + cur);
+            const uint32_t *lst = p.links_up + ((size_t)base + (uint32_t)(level - 1)) * p.maxM;
+            int cnt = 0;  // lists are dense: valid slots are 0..cnt-1
+            for (uint32_t b0 = 0; b0 < p.maxM; b0 += kTeam) {
+                uint32_t nid = kEmpty;
+                if (b0 + tid < p.maxM) {
+                    nid = __ldg(lst + b0 + tid);
+                    ids[b0 + tid] = nid;
+                }
+                cnt += __syncthreads_count(nid != kEmpty);
+            }
+            eval_list<LPV, CPL, METRIC>(q, p.vec, d4, ids, cnt, dist, grp, sub);
+            __syncthreads();
+            wD += cnt;
+            wHup += 1;
+            if (tid < 32) {  // argmin, lowest slot wins ties (sequential strict '<' scan, hnswalg.h:1289-1300)
+                float bd = 3.402823466e+38f;
+                int bj = 0x7fffffff;
+                for (int j = lane; j < cnt; j += 32) {
+                    const float dj = dist[j];
+                    if (dj < bd) { bd = dj; bj = j; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                    if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+                }
+                if (lane == 0) s_best = (cnt > 0 && bd < curdist) ? bj : -1;
+            }
+            __syncthreads();
+            const int b = s_best;
+            if (b >= 0) {
+                curdist = dist[b];
+                cur = ids[b];
+                changed = true;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- searchBaseLayerST: sorted top-ef buffer with expanded bits ----
+    int cb = 0;            // current buffer
+    int size = 1;          // entries in buf[cb]
+    if (tid == 0) {
+        buf_a[0] = make_key(curdist, cur);
+        hash_insert(hash, p.hash_bits, cur);
+        s_next = 0;
+    }
+    uint32_t hcount = 1;   // ids in the visited table (uniform across threads)
+    __syncthreads();
+
+    for (;;) {
+        const int next = s_next;
+        if (next >= size) break;
+        uint64_t *src = cb ? buf_b : buf_a, *dst = cb ? buf_a : buf_b;
+        const uint32_t node = (uint32_t)src[next] & kIdMask;
+        const float bound = (uint32_t)size == ef ? ord2f((uint32_t)(src[ef - 1] >> 32)) : 3.402823466e+38f;
+        const bool full = (uint32_t)size == ef;
+        __syncthreads();  // everyone has read s_next / src[next] before they are rewritten
+        if (tid == 0) {
+            src[next] |= (uint64_t)kExpanded;
+            s_cnt = 0;
+            s_next = 0x7fffffff;
+        }
+        // visited table at > 1/2 load: rebuild it from the buffer (results unchanged, see header)
+        if (hcount > HS / 2) {
+            for (uint32_t i = tid; i < HS; i += kTeam) hash[i] = kEmpty;
+            __syncthreads();
+            for (int i = tid; i < size; i += kTeam) hash_insert(hash, p.hash_bits, (uint32_t)src[i] & kIdMask);
+            hcount = size;
+            wReset += 1;
+        }
+        __syncthreads();
+
+        // neighbour list of the expanded node -> unvisited ids, compacted into ids[]
+        for (uint32_t b0 = 0; b0 < p.maxM0; b0 += kTeam) {
+            uint32_t nid = kEmpty;
+            if (b0 + tid < p.maxM0) nid = __ldg(p.links0 + (size_t)node * p.maxM0 + b0 + tid);
+            bool isnew = false;
+            if (nid != kEmpty) isnew = hash_insert(hash, p.hash_bits, nid);
+            const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+            int basepos = 0;
+            if (lane == 0 && m) basepos = atomicAdd(&s_cnt, __popc(m));
+            basepos = __shfl_sync(0xffffffffu, basepos, 0);
+            if (isnew) ids[basepos + __popc(m & ((1u << lane) - 1u))] = nid;
+        }
+        __syncthreads();
+        const int nnew = s_cnt;
+        wH0 += 1;
+        wD += nnew;
+        hcount += nnew;
+        eval_list<LPV, CPL, METRIC>(q, p.vec, d4, ids, nnew, dist, grp, sub);
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        // admit against the pre-expansion bound (hnswalg.h:395: size < ef || lowerBound > dist)
+        for (int b0 = 0; b0 < nnew; b0 += kTeam) {
+            bool ok = false;
+            uint64_t key = 0;
+            if (b0 + tid < nnew) {
+                const float dj = dist[b0 + tid];
+                ok = !full || dj < bound;
+                key = make_key(dj, ids[b0 + tid]);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            int basepos = 0;
+            if (lane == 0 && m) basepos = atomicAdd(&s_cnt, __popc(m));
+            basepos = __shfl_sync(0xffffffffu, basepos, 0);
+            if (ok) acc[basepos + __popc(m & ((1u << lane) - 1u))] = key;
+        }
+        __syncthreads();
+        const int m = s_cnt;
+        int local_min = 0x7fffffff;
+        if (m == 0) {
+            // nothing admitted: buffer unchanged, find the next unexpanded entry after `next`
+            for (int i = next + 1 + tid; i < size; i += kTeam)
+                if (!((uint32_t)src[i] & kExpanded)) { local_min = i; break; }
+        } else {
+            // merge by rank: final position = own index + number of smaller keys in the other list
+            for (int i = tid; i < size; i += kTeam) {
+                const uint64_t key = src[i];
+                const uint64_t km = key & kKeyMask;
+                int pos = i;
+                for (int j = 0; j < m; j++) pos += (acc[j] < km) ? 1 : 0;
+                if ((uint32_t)pos < ef) {
+                    dst[pos] = key;
+                    if (!((uint32_t)key & kExpanded)) local_min = min(local_min, pos);
+                }
+            }
+            for (int j = kTeam - 1 - tid; j < m; j += kTeam) {
+                const uint64_t key = acc[j];
+                int r = 0;
+                for (int i = 0; i < m; i++) r += (acc[i] < key) ? 1 : 0;
+                int lo = 0, hi = size;  // upper bound: equal keys (impossible by construction) stay distinct
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((src[mid] & kKeyMask) <= key) lo = mid + 1; else hi = mid;
+                }
+                const int pos = r + lo;
+                if ((uint32_t)pos < ef) {
+                    dst[pos] = key;
+                    local_min = min(local_min, pos);
+                }
+            }
+            size = min((int)ef, size + m);
+            cb ^= 1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));
+        if (lane == 0 && local_min != 0x7fffffff) atomicMin(&s_next, local_min);
+        __syncthreads();
+    }
+
+    // ---- epilogue: first k entries are the result, closest first (hnswalg.h:1315-1322) ----
+    const uint64_t *res = cb ? buf_b : buf_a;
+    for (uint32_t j = tid; j < p.k; j += kTeam) {
+        uint64_t lab = 0xFFFFFFFFFFFFFFFFull;
+        float dj = __int_as_float(0x7f800000);
+        if (j < (uint32_t)size) {
+            const uint64_t key = res[j];
+            lab = __ldg(p.labels + ((uint32_t)key & kIdMask));
+            dj = ord2f((uint32_t)(key >> 32));
+        }
+        p.out_labels[(size_t)qi * p.k + j] = lab;
+        p.out_dists[(size_t)qi * p.k + j] = dj;
+    }
+    if (tid == 0) {
+        if (p.out_counts) p.out_counts[qi] = min((uint32_t)size, p.k);
+        if (p.out_work) {
+            uint32_t *w = p.out_work + (size_t)qi * 4;
+            w[0] = wD; w[1] = wH0; w[2] = wHup; w[3] = wReset;
+        }
+    }
+}
+
+// k-way merge of per-shard results: one warp per query over shards*k candidates.
+static __global__ void merge_topk_kernel(const uint64_t *__restrict__ labels_in, const float *__restrict__ dists_in,
+                                  uint32_t shards, uint32_t nq, uint32_t k, uint64_t *__restrict__ labels_out,
+                                  float *__restrict__ dists_out) {
+    const uint32_t qi = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const uint32_t total = shards * k;
+    // rank of every candidate among all candidates by (dist, label); O(total^2/32) per warp, total <= 8*100
+    for (uint32_t c = lane; c < total; c += 32) {
+        const uint32_t s = c / k, j = c % k;
+        const float dc = dists_in[((size_t)s * nq + qi) * k + j];
+        const uint64_t lc = labels_in[((size_t)s * nq + qi) * k + j];
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < total; o++) {
+            const uint32_t so = o / k, jo = o % k;
+            const float d2 = dists_in[((size_t)so * nq + qi) * k + jo];
+            const uint64_t l2 = labels_in[((size_t)so * nq + qi) * k + jo];
+            rank += (d2 < dc || (d2 == dc && (l2 < lc || (l2 == lc && o < c)))) ? 1u : 0u;
+        }
+        if (rank < k) {
+            labels_out[(size_t)qi * k + rank] = lc;
+            dists_out[(size_t)qi * k + rank] = dc;
+        }
+    }
+}
+
+}  // namespace b200

@@ -1,0 +1,72 @@
+"""GPU parity: BruteforceSearch through the C ABI.  Bar: ids bit-exact (ties broken by id), distances within 1e-5
+relative -- the exact-scan kernel sums in the reference's SSE lane order, so they are in fact bit-identical."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import gauss
+from oracle import bind
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("metric,n,d,k", [(bind.L2, 5000, 128, 10), (bind.IP, 3000, 96, 100), (bind.L2, 2000, 30, 7),
+                                          (bind.IP, 1500, 17, 3), (bind.L2, 700, 3, 5), (bind.IP, 4097, 768, 100)])
+def test_exact_vs_oracle(lib, orc, ref, metric, n, d, k):
+    X = gauss(21, n, d)
+    if metric == bind.IP:
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+    X[n // 2] = X[n // 3]  # exact duplicate rows -> equal distances, order decided by label
+    Q = gauss(22, 130, d)
+    labels = (np.arange(n, dtype=np.uint64) * 7 + 3)
+    space = lib.L2Space(d) if metric == bind.L2 else lib.InnerProductSpace(d)
+    g = lib.BruteforceSearch(space, n)
+    g.addPoints(X, labels)
+    c = orc.bf_new(metric, d, n)
+    c.add(X, labels)
+    rg, rc = g.searchKnnBatch(Q, k), c.search(Q, k)
+    assert np.array_equal(rg["labels"], rc["labels"])
+    assert np.array_equal(rg["dists"], rc["dists"])
+    assert np.array_equal(rg["counts"], rc["counts"])
+    if ref is not None:
+        r = ref.bf_new(metric, d, n)
+        r.add(X, labels)
+        rr = r.search(Q, k)
+        assert np.array_equal(rg["labels"], rr["labels"]) and np.array_equal(rg["dists"], rr["dists"])
+
+
+def test_add_overwrite_remove_save_load(lib, orc, tmp_path):
+    d, n = 20, 600
+    X = gauss(31, n, d)
+    Q = gauss(32, 40, d)
+    g = lib.BruteforceSearch(lib.L2Space(d), n)
+    c = orc.bf_new(bind.L2, d, n)
+    for eng in (g, c):
+        add = eng.addPoints if eng is g else eng.add
+        add(X[:500])
+        add(X[500:510], np.arange(10, 20, dtype=np.uint64))       # existing labels: rows overwritten
+        (eng.removePoint if eng is g else eng.remove)(3)           # last row swapped in
+        (eng.removePoint if eng is g else eng.remove)(499)
+    assert g.cur_element_count == c.count() == 498
+    rg, rc = g.searchKnnBatch(Q, 12), c.search(Q, 12)
+    assert np.array_equal(rg["labels"], rc["labels"]) and np.array_equal(rg["dists"], rc["dists"])
+    pg, pc = str(tmp_path / "g.bin"), str(tmp_path / "c.bin")
+    g.saveIndex(pg)
+    c.save(pc)
+    sha = lambda p: hashlib.sha256(open(p, "rb").read()).hexdigest()
+    assert sha(pg) == sha(pc)
+    g2 = lib.BruteforceSearch(lib.L2Space(d), pg)
+    r2 = g2.searchKnnBatch(Q, 12)
+    assert np.array_equal(r2["labels"], rc["labels"])
+    with pytest.raises(lib.B200Error, match="exceeds the specified limit"):
+        g.addPoints(gauss(33, 200, d), np.arange(10_000, 10_200, dtype=np.uint64))
+
+
+def test_k_larger_than_count(lib):
+    g = lib.BruteforceSearch(lib.L2Space(4), 10)
+    X = np.eye(4, dtype=np.float32)[:3]
+    g.addPoints(X)
+    r = g.searchKnnBatch(X[:1], 6)
+    assert r["counts"][0] == 3 and r["labels"][0, :3].tolist() == [0, 1, 2]
+    assert np.isinf(r["dists"][0, 3:]).all()

@@ -1,0 +1,134 @@
+"""GPU parity: batched searchKnn through the C ABI vs the oracle (and the compiled reference when present) on the
+same reference-format graphs.  Bars (BASELINE.json north_star): identical id sets on >= 99 % of queries, recall@10
+within 0.5 pt, distances within 1e-5 relative; work counters equal evaluation for evaluation."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import bind
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5  # relative distance tolerance (fp32 warp reduction vs the reference's SSE summation order)
+
+
+def _space(lib, metric, d):
+    return lib.L2Space(d) if metric == bind.L2 else lib.InnerProductSpace(d)
+
+
+def _same_sets(a, b):
+    return np.array([set(x) == set(y) for x, y in zip(a.tolist(), b.tolist())])
+
+
+def _check(gpu, cpu, name):
+    same = _same_sets(gpu["labels"], cpu["labels"])
+    assert same.mean() >= 0.99, (name, same.mean())
+    assert np.array_equal(gpu["counts"], cpu["counts"])
+    ok = same & (gpu["labels"] == cpu["labels"]).all(axis=1)
+    d1, d2 = gpu["dists"][ok], cpu["dists"][ok]
+    fin = np.isfinite(d2)
+    assert np.all(np.abs(d1[fin] - d2[fin]) <= REL_TOL * np.maximum(1.0, np.abs(d2[fin]))), name
+    return same.mean()
+
+
+@pytest.mark.parametrize("name", ["l2_n2000_d16_M8", "ip_n1500_d24_M6", "l2_n1200_d13_M5"])
+def test_golden_reference_dumps(lib, golden, name):
+    """Graph and expected results both come from the unmodified reference (tests/golden/make_golden.py)."""
+    meta, g = golden
+    m = meta[name]
+    idx = lib.HierarchicalNSW(_space(lib, m["metric"], m["d"]), os.path.join(GOLDEN, name + ".bin"))
+    assert idx.cur_element_count == m["n"] and idx.maxlevel_ == m["maxlevel"] and idx.enterpoint_node_ == m["enterpoint"]
+    Q = g[name + "/Q"]
+    for ef in m["efs"]:
+        r = idx.searchKnnBatch(Q, 10, ef=ef, work=True)
+        cpu = dict(labels=g["%s/ef%d/labels" % (name, ef)], dists=g["%s/ef%d/dists" % (name, ef)],
+                   counts=np.full(len(Q), 10, np.uint32))
+        _check(r, cpu, (name, ef))
+        assert r["resets"].sum() == 0
+        # the reference evaluates the base-layer entry point twice (hnswalg.h:1276 and :327); we reuse it
+        assert np.array_equal(r["D"] + 1, g["%s/ef%d/D" % (name, ef)])
+        assert np.array_equal(r["Hup"], g["%s/ef%d/Hup" % (name, ef)])
+
+
+@pytest.mark.parametrize("name", ["l2_d128", "l2_d100", "l2_d30", "ip_d96", "ip_d17", "lowrank_d128"])
+def test_parity_vs_oracle(lib, orc, ref, graphs, name):
+    s = graphs[name]
+    idx = lib.HierarchicalNSW(_space(lib, s["metric"], s["d"]), s["path"])
+    cpu_idx = orc.hnsw_load(s["metric"], s["d"], s["path"])
+    bf = orc.bf_new(s["metric"], s["d"], s["n"])
+    bf.add(s["X"])
+    gt = bf.search(s["Q"], 10)["labels"]
+    for ef in (10, 32, 64, 200):
+        r = idx.searchKnnBatch(s["Q"], 10, ef=ef, work=True)
+        c = cpu_idx.search(s["Q"], 10, ef)
+        _check(r, c, (name, ef))
+        rec_g = np.mean([len(set(a) & set(b)) for a, b in zip(r["labels"].tolist(), gt.tolist())]) / 10
+        rec_c = np.mean([len(set(a) & set(b)) for a, b in zip(c["labels"].tolist(), gt.tolist())]) / 10
+        assert abs(rec_g - rec_c) <= 0.005, (name, ef, rec_g, rec_c)
+        nz = r["resets"] == 0
+        assert np.array_equal(r["D"][nz] + 1, c["D"][nz]), (name, ef)
+        assert np.array_equal(r["H0"][nz], c["H0"][nz])
+        assert np.array_equal(r["Hup"], c["Hup"])
+    if ref is not None:  # the real reference on the same file
+        rr = ref.hnsw_load(s["metric"], s["d"], s["path"]).search(s["Q"], 10, 64)
+        _check(idx.searchKnnBatch(s["Q"], 10, ef=64), rr, (name, "ref"))
+
+
+def test_setef_k_and_padding(lib, orc, graphs):
+    s = graphs["l2_d30"]
+    idx = lib.HierarchicalNSW(lib.L2Space(s["d"]), s["path"])
+    cpu = orc.hnsw_load(s["metric"], s["d"], s["path"])
+    assert idx.info()["ef"] == 10                      # loadIndex resets ef_ to 10 (hnswalg.h:795)
+    idx.setEf(50)
+    _check(idx.searchKnnBatch(s["Q"], 5), cpu.search(s["Q"], 5, 50), "setEf")
+    # ef < k -> max(ef, k) (hnswalg.h:1309)
+    _check(idx.searchKnnBatch(s["Q"][:50], 100, ef=10), cpu.search(s["Q"][:50], 100, 10), "ef<k")
+    # single-query API: furthest first like the reference's priority_queue
+    one = idx.searchKnn(s["Q"][0], 7)
+    c1 = cpu.search(s["Q"][:1], 7, 50)
+    assert [l for _, l in one] == c1["labels"][0][::-1].tolist()
+    # k larger than the index: padded with UINT64_MAX / +inf
+    tiny = orc.hnsw_new(bind.L2, 8, 5, 4, 10)
+    X = np.random.default_rng(0).standard_normal((5, 8), dtype=np.float32)
+    tiny.add(X)
+    p = s["path"] + ".tiny"
+    tiny.save(p)
+    t = lib.HierarchicalNSW(lib.L2Space(8), p)
+    r = t.searchKnnBatch(X[:2], 8, ef=16)
+    assert r["counts"].tolist() == [5, 5]
+    assert (r["labels"][:, 5:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and np.isinf(r["dists"][:, 5:]).all()
+    assert r["labels"][0, 0] == 0 and r["labels"][1, 0] == 1
+
+
+def test_empty_index_and_save_roundtrip(lib, graphs, tmp_path):
+    e = lib.HierarchicalNSW(lib.L2Space(16), 100, 8, 50)
+    r = e.searchKnnBatch(np.zeros((3, 16), np.float32), 4)
+    assert r["counts"].tolist() == [0, 0, 0] and np.isinf(r["dists"]).all()   # hnswalg.h:1273
+    s = graphs["ip_d96"]
+    idx = lib.HierarchicalNSW(lib.InnerProductSpace(s["d"]), s["path"])
+    out = str(tmp_path / "resaved.bin")
+    idx.saveIndex(out)
+    sha = lambda p: hashlib.sha256(open(p, "rb").read()).hexdigest()
+    assert sha(out) == sha(s["path"])
+    assert idx.indexFileSize() == os.path.getsize(s["path"])
+    # accessors the reference's consumers use (build.cpp:51-99)
+    lv = idx.element_levels_
+    assert lv.shape[0] == s["n"] and lv.max() == idx.maxlevel_
+    assert idx.getExternalLabel(17) == 17
+    assert np.array_equal(idx.getDataByLabel(17), s["X"][17])
+    top = int(np.argmax(lv))
+    assert len(idx.get_linklist_at_level(top, int(lv[top]))) <= s["M"]
+
+
+def test_visited_table_rebuild_keeps_results(lib, orc, graphs, monkeypatch):
+    """A deliberately tiny visited table forces rebuilds; results must not change (only D grows)."""
+    s = graphs["l2_d128"]
+    cpu = orc.hnsw_load(s["metric"], s["d"], s["path"]).search(s["Q"], 10, 128)
+    monkeypatch.setenv("B200HNSW_HASH_BITS", "9")
+    idx = lib.HierarchicalNSW(lib.L2Space(s["d"]), s["path"])
+    r = idx.searchKnnBatch(s["Q"], 10, ef=128, work=True)
+    assert r["resets"].sum() > 0
+    _check(r, cpu, "rebuild")
+    assert (r["D"] + 1 >= cpu["D"]).all()
