@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: QPS @ recall@10 >= 0.95 of batched searchKnn (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1], "C2"): synthetic SIFT-shaped 1M x 128 fp32, L2, M=32, ef_construction=200,
+batches of 10 000 queries, k=10; ef = the smallest value of the sweep whose recall@10 (exact ground truth, first
+1000 queries) is >= 0.95.  A "step" is one batch of 10 000 queries through the hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm  (CUDA kernels through the C ABI)
+  python bench.py --impl reference ...                           reference arm (unmodified hnswlib on host cores)
+
+N > 1 (torchrun, one rank per GPU): the data set is sharded, one 1M-point sub-index per GPU (weak scaling), every
+rank searches the same query batch, per-shard top-k are exchanged with an NCCL all_gather and merged on the GPU
+(SURVEY.md 8(e)).  `value` counts shard-level searches (N x nq per step); merged queries/s is value / N.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EF_SWEEP = [12, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128, 192, 256]
+CACHE = os.environ.get("B200HNSW_CACHE", "/tmp/b200hnsw_cache")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="points per GPU (shard size)")
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--M", type=int, default=32)
+    ap.add_argument("--efc", type=int, default=200)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--ef", type=int, default=0, help="override the recall-driven ef selection")
+    ap.add_argument("--recall", type=float, default=0.95)
+    ap.add_argument("--batches", type=int, default=4, help="distinct query batches cycled through the steps")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def recall_at_k(labels, gt):
+    return float(np.mean([len(set(a) & set(b)) for a, b in zip(labels.tolist(), gt.tolist())]) / gt.shape[1])
+
+
+def workload_name(a):
+    return ("C2: synthetic SIFT-shaped (rank-16 + 0.1 noise) %dx%d fp32 L2, M=%d ef_construction=%d, batched searchKnn "
+            "%d queries k=%d" % (a.n, a.dim, a.M, a.efc, a.nq, a.k))
+
+
+def shard_data(a, rank):
+    from research_new_hnsw_b200.synth import lowrank_data
+    return lowrank_data(a.n, a.dim, seed=1 + 1000 * rank)
+
+
+def query_batches(a):
+    from research_new_hnsw_b200.synth import lowrank_data
+    return [lowrank_data(a.nq, a.dim, seed=2 + 7 * b) for b in range(max(1, a.batches))]
+
+
+def graph_path(a, rank):
+    os.makedirs(CACHE, exist_ok=True)
+    return os.path.join(CACHE, "c2_n%d_d%d_M%d_efc%d_r%d.bin" % (a.n, a.dim, a.M, a.efc, rank))
+
+
+def build_graph_with_reference(a, rank, X, threads):
+    """The graph both arms search is the reference's own (multi-threaded addPoint + saveIndex); cached on disk so the
+    two arms of one driver run share it."""
+    from oracle import bind
+    path = graph_path(a, rank)
+    if os.path.exists(path) and os.path.getsize(path) > 96 + a.n * (a.dim * 4 + 8 * a.M + 12):
+        return path, 0.0
+    ref = bind.Ref(bind.best_ref_level())
+    idx = ref.hnsw_new(bind.L2, a.dim, a.n, a.M, a.efc)
+    labels = np.arange(a.n, dtype=np.uint64) + np.uint64(rank * a.n)
+    sec = idx.add(X, labels, threads=threads)
+    tmp = path + ".tmp%d" % os.getpid()
+    idx.save(tmp)
+    os.replace(tmp, path)
+    return path, sec
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (nvidia-smi's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if self.is_alive():
+            self.join(timeout=1)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def algorithmic_bytes(a, work):
+    """B_q = D*d*4 + H0*(4+4*maxM0) + Hup*(4+4*maxM) + 4d + 12k, summed over the batch (counted)."""
+    D, H0, Hup = int(work[:, 0].sum()), int(work[:, 1].sum()), int(work[:, 2].sum())
+    return D * a.dim * 4 + H0 * (4 + 8 * a.M) + Hup * (4 + 4 * a.M) + work.shape[0] * (4 * a.dim + 12 * a.k), D, H0, Hup
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_leg(a, path, batches, ef, budget_s, threads):
+    """Unmodified reference (oracle/_ref) on the host cores: the hnsw_service pattern, T threads looping searchKnn."""
+    from oracle import bind
+    level = bind.best_ref_level()
+    ref = bind.Ref(level)
+    idx = ref.hnsw_load(bind.L2, a.dim, path)
+    idx.search(batches[0][:2000], a.k, ef, threads=threads)  # warm-up: per-thread VisitedList allocation
+    done, sec, i = 0, 0.0, 0
+    while sec < budget_s and i < 64:
+        r = idx.search(batches[i % len(batches)], a.k, ef, threads=threads)
+        sec += r["seconds"]
+        done += a.nq
+        i += 1
+    return dict(value=done / sec, unit="queries/s", cores=threads, kind="reference",
+                sample="%d batches of %d queries, ef=%d, reference built -O3 %s, %d threads looping searchKnn"
+                       % (i, a.nq, ef, level, threads)), idx
+
+
+def pick_ef(a, search_fn, gt1000, Qs):
+    if a.ef:
+        r = search_fn(Qs, a.ef)
+        return a.ef, recall_at_k(r, gt1000), {a.ef: recall_at_k(r, gt1000)}
+    table = {}
+    for ef in EF_SWEEP:
+        if ef < a.k:
+            continue
+        rec = recall_at_k(search_fn(Qs, ef), gt1000)
+        table[ef] = round(rec, 4)
+        if rec >= a.recall:
+            return ef, rec, table
+    return EF_SWEEP[-1], rec, table
+
+
+def run_reference(a, rank, world):
+    if rank != 0:
+        return
+    from oracle import bind
+    threads = os.cpu_count() or 1
+    X = shard_data(a, 0)
+    batches = query_batches(a)
+    path, build_s = build_graph_with_reference(a, 0, X, threads)
+    ref = bind.Ref(bind.best_ref_level())
+    bf = ref.bf_new(bind.L2, a.dim, a.n)
+    bf.add(X)
+    Qs = batches[0][:1000]
+    gt = bf.search(Qs, a.k, threads=threads)["labels"]
+    del bf
+    idx = ref.hnsw_load(bind.L2, a.dim, path)
+    ef, rec, table = pick_ef(a, lambda Q, e: idx.search(Q, a.k, e, threads=threads)["labels"], gt, Qs)
+    for _ in range(a.warmup):
+        idx.search(batches[0][:2000], a.k, ef, threads=threads)
+    sec = 0.0
+    # each step = a bounded sample of the batch so the whole run stays within minutes even on few cores
+    sample = min(a.nq, 10_000)
+    for s in range(a.steps):
+        sec += idx.search(batches[s % len(batches)][:sample], a.k, ef, threads=threads)["seconds"]
+    qps = a.steps * sample / sec
+    line = {"impl": "reference", "metric": "QPS @ recall@10>=0.95, 1Mx128 L2", "value": qps, "unit": "queries/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
+                       "graph": "built by the reference (addPoint, %d threads)%s" %
+                                (threads, "" if build_s == 0 else " in %.1f s = %.0f points/s" % (build_s, a.n / build_s)),
+                       "step": "%d queries of the batch" % sample},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
+                             "sample": "%d queries per step, ef=%d, -O3 %s build of the unmodified headers"
+                                       % (sample, ef, bind.best_ref_level())},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a, rank, local_rank, world):
+    import torch
+    import research_new_hnsw_b200 as pkg
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    threads = max(1, (os.cpu_count() or 1) // world)
+    X = shard_data(a, rank)
+    batches = query_batches(a)
+    path, build_s = build_graph_with_reference(a, rank, X, threads)
+    t0 = time.time()
+    idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), path, device=local_rank)
+    load_s = time.time() - t0
+
+    # exact ground truth for the first 1000 queries from the exact-scan kernel (global over all shards when N > 1)
+    Qs = batches[0][:1000]
+    bf = pkg.BruteforceSearch(pkg.L2Space(a.dim), a.n, device=local_rank)
+    bf.addPoints(X, np.arange(a.n, dtype=np.uint64) + np.uint64(rank * a.n))
+    g = bf.searchKnnBatch(Qs, a.k)
+    del bf, X
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def merged(labels_t, dists_t, nq):
+        """all_gather per-shard rows + GPU k-way merge; identity at world == 1."""
+        if world == 1:
+            return labels_t, dists_t
+        gl = torch.empty((world,) + tuple(labels_t.shape), dtype=torch.int64, device=dev)
+        gd = torch.empty((world,) + tuple(dists_t.shape), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gl, labels_t)
+        dist.all_gather_into_tensor(gd, dists_t)
+        ol, od = torch.empty_like(labels_t), torch.empty_like(dists_t)
+        pkg.merge_topk_device(gl.data_ptr(), gd.data_ptr(), world, nq, a.k, ol.data_ptr(), od.data_ptr(), stream)
+        return ol, od
+
+    gt_l = torch.from_numpy(g["labels"].view(np.int64)).to(dev)
+    gt_d = torch.from_numpy(g["dists"]).to(dev)
+    gt_l, _ = merged(gt_l, gt_d, len(Qs))
+    gt = gt_l.cpu().numpy().view(np.uint64)
+
+    def dev_search(dQ, nq, ef, work=None):
+        ol = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
+        od = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
+        idx.searchKnnDevice(dQ.data_ptr(), nq, a.k, ef, ol.data_ptr(), od.data_ptr(), 0,
+                            work.data_ptr() if work is not None else 0, stream)
+        return merged(ol, od, nq)
+
+    dQs = torch.from_numpy(Qs).to(dev)
+
+    def sweep_fn(Q, ef):
+        ol, _ = dev_search(dQs, len(Qs), ef)
+        torch.cuda.synchronize()
+        return ol.cpu().numpy().view(np.uint64)
+
+    ef, rec, table = pick_ef(a, sweep_fn, gt, Qs)
+    if world > 1:  # every rank must use the same ef
+        t = torch.tensor([ef], device=dev)
+        dist.broadcast(t, 0)
+        ef = int(t.item())
+
+    dbatches = [torch.from_numpy(b).to(dev) for b in batches]
+    # counted work of every batch (outside the timed region; identical launches)
+    works = []
+    for dQ in dbatches:
+        w = torch.zeros((a.nq, 4), dtype=torch.int32, device=dev)
+        dev_search(dQ, a.nq, ef, w)
+        torch.cuda.synchronize()
+        works.append(w.cpu().numpy().astype(np.int64))
+    for s in range(a.warmup):
+        dev_search(dbatches[s % len(dbatches)], a.nq, ef)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for s in range(a.steps):
+        dev_search(dbatches[s % len(dbatches)], a.nq, ef)
+    ev1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.result()
+    ms_total = ev0.elapsed_time(ev1)
+    # search-kernel-only timing (same launches, no collective) for the roofline
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ol = torch.empty((a.nq, a.k), dtype=torch.int64, device=dev)
+    od = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    k0.record()
+    for s in range(a.steps):
+        idx.searchKnnDevice(dbatches[s % len(dbatches)].data_ptr(), a.nq, a.k, ef, ol.data_ptr(), od.data_ptr(), 0, 0,
+                            stream)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / a.steps
+    if dist:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + kernel + D2H inside the timed region
+    hq = [torch.from_numpy(b).pin_memory() for b in batches]
+    for s in range(max(3, a.warmup)):
+        idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef)
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        r = idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef)
+        if world > 1:
+            merged(torch.from_numpy(r["labels"].view(np.int64)).to(dev), torch.from_numpy(r["dists"]).to(dev), a.nq)
+            torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = a.nq * a.dim * 4
+    d2h = a.nq * a.k * 12 + a.nq * 4 + a.nq * 16
+
+    if rank == 0:
+        bytes_sum = [algorithmic_bytes(a, w) for w in works]
+        per_launch = float(np.mean([b[0] for b in bytes_sum]))
+        peak, peak_src = peaks()
+        achieved = per_launch / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "search_kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        resets = int(sum(w[:, 3].sum() for w in works))
+        cpu_leg = None
+        try:
+            cpu_leg, _ = cpu_reference_leg(a, path, batches, ef, a.cpu_seconds, os.cpu_count() or 1)
+        except Exception as e:  # the checker binary is missing: report it, never substitute
+            cpu_leg = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        line = {
+            "metric": "QPS @ recall@10>=0.95, 1Mx128 L2", "value": world * a.nq * a.steps / (ms_total * 1e-3),
+            "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
+                       "parallelism": "1 GPU" if world == 1 else
+                       "shard%d: one %d-point sub-index per GPU, queries replicated, NCCL all_gather + GPU merge; value "
+                       "counts shard-level searches (merged queries/s = value/%d)" % (world, a.n, world),
+                       "l2_policy": "inputs larger than L2 (index %.0f MB vs 126 MB L2); %d distinct query batches cycled"
+                                    % ((a.n * (a.dim * 4 + 8 * a.M)) / 1e6, len(batches)),
+                       "graph": "reference-built saveIndex file%s, loaded in %.1f s" %
+                                ("" if build_s == 0 else " (%.1f s, %.0f points/s on %d threads)" % (build_s, a.n / build_s, threads),
+                                 load_s),
+                       "visited_table_rebuilds_per_batch": resets / len(works)},
+            "clocks": clocks,
+            "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "api": "b200hnsw_search_batch (host pointers, pinned)"},
+            "gpu_launches": a.steps * (1 if world == 1 else 2),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "hnsw_search_kernel<8,4,L2>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src,
+                         "per_query": {"D": bytes_sum[0][1] / a.nq, "H0": bytes_sum[0][2] / a.nq,
+                                       "Hup": bytes_sum[0][3] / a.nq}},
+            "cpu_baseline": cpu_leg,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+    else:
+        run_b200(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

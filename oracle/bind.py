@@ -402,20 +402,7 @@ class OrcBF:
         return dict(labels=labels, dists=dists, counts=counts, seconds=sec.value)
 
 
-# ---------------------------------------------------------------------------------------------
-# Synthetic data laws.  Pure numpy so they are identical here and on the GPU box.
-# ---------------------------------------------------------------------------------------------
-def lowrank_data(n, d, seed, latent=16, noise=0.1, proj_seed=123, normalize=False):
-    """'SIFT-shaped' / 'Deep-shaped' rows: z ~ N(0,I_latent), x = z A + noise * eps (A fixed by proj_seed)."""
-    A = np.random.default_rng(proj_seed).standard_normal((latent, d), dtype=np.float32)
-    rng = np.random.default_rng(seed)
-    out = np.empty((n, d), np.float32)
-    step = 1 << 18
-    for s in range(0, n, step):
-        e = min(n, s + step)
-        z = rng.standard_normal((e - s, latent), dtype=np.float32)
-        x = z @ A + np.float32(noise) * rng.standard_normal((e - s, d), dtype=np.float32)
-        if normalize:
-            x /= np.linalg.norm(x, axis=1, keepdims=True)
-        out[s:e] = x
-    return out
+# Synthetic data laws live with the product (research_new_hnsw_b200/synth.py); re-exported for the tests.
+def lowrank_data(*args, **kw):
+    from research_new_hnsw_b200.synth import lowrank_data as f
+    return f(*args, **kw)

@@ -184,8 +184,13 @@ static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
     int d = 0;
     cudaGetDevice(&d);
     if (d < 16 && !configured[d]) {
+        cudaFuncAttributes fa;
+        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<LPV, CPL, METRIC>));
+        int optin = 0;
+        B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
         B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<LPV, CPL, METRIC>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
     hnsw_search_kernel<LPV, CPL, METRIC><<<a.nq, kTeam, smem, st>>>(a);
@@ -242,8 +247,8 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.nq = (uint32_t)nq; a.k = (uint32_t)k; a.ef = (uint32_t)efx;
     a.hash_bits = pick_hash_bits(efx, list_cap);
     const SearchSmem L(a.ef, (uint32_t)list_cap, a.d4, a.hash_bits);
-    if (L.total > 227 * 1024) {
-        set_error("search configuration needs more than 227 KB of shared memory");
+    if (L.total > 226 * 1024) {
+        set_error("search configuration needs more than 226 KB of shared memory");
         return B200HNSW_E_UNSUPPORTED;
     }
     stats.kernel_launches += 1;
