@@ -106,7 +106,8 @@ int b200hnsw_load(const char *path, const b200hnsw_params *params, b200hnsw_inde
 int b200hnsw_save(b200hnsw_index *h, const char *path) {
     B200_GUARD_BEGIN
     if (!h || !path) { set_error("null argument"); return B200HNSW_E_ARG; }
-    int rc = b200hnsw_flush(h);
+    int rc = h->ix.flush();
+    if (!rc) rc = h->ix.sync_host_mirror();
     if (rc) return rc;
     if (h->ix.host.save(path)) { set_error("Cannot open file"); return B200HNSW_E_OPEN; }
     return 0;
@@ -180,6 +181,7 @@ int b200hnsw_get_linklist(b200hnsw_index *h, uint32_t id, int level, const uint3
     B200_GUARD_BEGIN
     if (!h || !ptr_out) { set_error("null argument"); return B200HNSW_E_ARG; }
     int rc = h->ix.flush();
+    if (!rc) rc = h->ix.sync_host_mirror();
     if (rc) return rc;
     const b200::HostImage &m = h->ix.host;
     if (id >= m.cur || level < 0 || level > m.levels[id]) { set_error("no such link list"); return B200HNSW_E_ARG; }
@@ -249,6 +251,7 @@ int b200hnsw_resize(b200hnsw_index *h, size_t new_max) {  // hnswalg.h:633-656
         return B200HNSW_E_ARG;
     }
     int rc = h->ix.flush();
+    if (!rc) rc = h->ix.sync_host_mirror();
     if (rc) return rc;
     if (!h->ix.host.resize(new_max)) {
         set_error("Not enough memory: resizeIndex failed to allocate base layer");

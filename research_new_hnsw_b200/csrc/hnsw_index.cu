@@ -10,6 +10,7 @@ HnswIndex::~HnswIndex() {
     if (dev.cap || dev.err_flag) {
         cudaSetDevice(dev.device);
         dev.release();
+        bld.release();
     }
     cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
     if (ev0) cudaEventDestroy(ev0);
@@ -41,6 +42,7 @@ int HnswIndex::init_device() {
 int HnswIndex::alloc_device(size_t cap) {
     B200_CUDA_OK(cudaSetDevice(dev.device));
     dev.release();
+    bld.release();
     dev.cap = cap;
     dev.dim = host.dim;
     dev.d4 = (host.dim + 3) / 4;
@@ -138,6 +140,9 @@ int HnswIndex::upload_all() {
         }
     }
     linked = n;
+    dev_entry = host.enterpoint;
+    dev_maxlevel = host.maxlevel;
+    mirror_dirty = false;
     return upload_upper();
 }
 
@@ -227,7 +232,7 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
         return B200HNSW_E_UNSUPPORTED;
     }
     B200_CUDA_OK(cudaSetDevice(dev.device));
-    if (host.cur == 0) {  // hnswalg.h:1273: empty index -> empty result
+    if (linked == 0) {  // hnswalg.h:1273: empty index -> empty result
         B200_CUDA_OK(cudaMemsetAsync(dl, 0xFF, nq * k * 8, st));
         fill_pad_rows(dd, dc, dw, nq, k, st);  // dist = +inf, counts = 0
         return 0;
@@ -242,7 +247,7 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     SearchArgs a{};
     a.vec = dev.vec; a.links0 = dev.links0; a.up_base = dev.up_base; a.links_up = dev.links_up;
     a.labels = dev.labels; a.Q = dQ_; a.out_labels = dl; a.out_dists = dd; a.out_counts = dc; a.out_work = dw;
-    a.n = (uint32_t)linked; a.entry = host.enterpoint; a.maxlevel = host.maxlevel;
+    a.n = (uint32_t)linked; a.entry = dev_entry; a.maxlevel = dev_maxlevel;
     a.dim = (uint32_t)host.dim; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)host.maxM; a.maxM0 = (uint32_t)host.maxM0;
     a.nq = (uint32_t)nq; a.k = (uint32_t)k; a.ef = (uint32_t)efx;
     a.hash_bits = pick_hash_bits(efx, list_cap);

@@ -8,6 +8,19 @@
 
 namespace b200 {
 
+// Device scratch of the batched graph build (build.cu); allocated on first flush.
+struct BuildScratch {
+    int32_t *plevel = nullptr;
+    uint64_t *cand = nullptr;
+    uint32_t *cand_cnt = nullptr, *list_off = nullptr, *list_point = nullptr, *list_level = nullptr;
+    uint32_t *incnt = nullptr;
+    uint64_t *incoming = nullptr;
+    uint32_t *aff_node = nullptr, *aff_level = nullptr, *aff_count = nullptr;
+    unsigned long long *work = nullptr;
+    size_t cand_efc = 0;
+    void release();
+};
+
 struct HnswIndex {
     b200hnsw_params prm{};
     HostImage host;
@@ -17,6 +30,10 @@ struct HnswIndex {
     b200hnsw_stats stats{};
     // staged insertions (add_batch before flush): ids [linked, host.cur) are not yet in the graph
     size_t linked = 0;
+    uint32_t dev_entry = (uint32_t)-1;  // entry point / max level of the linked part of the graph
+    int dev_maxlevel = -1;
+    bool mirror_dirty = false;          // device link lists are newer than the host mirror
+    BuildScratch bld;
     // scratch for the host-pointer search path
     float *dQ = nullptr;
     uint64_t *dLabels = nullptr;
@@ -39,6 +56,7 @@ struct HnswIndex {
     // build.cu: addPoint staging and the batched GPU graph build
     int add_batch(const float *X, const uint64_t *labels, size_t n);
     int flush();
+    int sync_host_mirror();
 };
 
 uint32_t pick_hash_bits(size_t ef, size_t list_cap);

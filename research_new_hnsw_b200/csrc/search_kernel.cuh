@@ -85,7 +85,7 @@ __device__ __forceinline__ float acc4(float acc, const float4 &q, const float4 &
 
 // Distances from the query (register slices q[]) to ids[0..n): each group of LPV lanes owns one vector at a time,
 // two vectors (2*CPL 128-bit loads per lane) are in flight per group.  dists[j] is written by the group leader.
-template <int LPV, int CPL, int METRIC>
+template <int LPV, int CPL, int METRIC, bool CACHED = false>
 __device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *__restrict__ vec, uint32_t d4,
                                           const uint32_t *ids, int n, float *dists, int grp, int sub) {
     constexpr int NGRP = kTeam / LPV;
@@ -99,12 +99,12 @@ __device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const uint32_t idx = sub + c * LPV;
-            va[c] = idx < d4 ? ldg_stream(ra + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            va[c] = idx < d4 ? (CACHED ? __ldg(ra + idx) : ldg_stream(ra + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const uint32_t idx = sub + c * LPV;
-            vb[c] = (has2 && idx < d4) ? ldg_stream(rb + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[c] = (has2 && idx < d4) ? (CACHED ? __ldg(rb + idx) : ldg_stream(rb + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float sa = 0.f, sb = 0.f;
 #pragma unroll
@@ -136,167 +136,170 @@ __device__ __forceinline__ bool hash_insert(uint32_t *tab, uint32_t bits, uint32
     }
 }
 
-template <int LPV, int CPL, int METRIC>
-__global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
-    const SearchSmem L(p.ef, list_cap, p.d4, p.hash_bits);
-    uint64_t *const buf_a = (uint64_t *)(smem + L.off_buf0), *const buf_b = (uint64_t *)(smem + L.off_buf1);
-    uint64_t *acc = (uint64_t *)(smem + L.off_acc);
-    uint32_t *ids = (uint32_t *)(smem + L.off_ids);
-    float *dist = (float *)(smem + L.off_dist);
-    float *qs = (float *)(smem + L.off_q);
-    uint32_t *hash = (uint32_t *)(smem + L.off_hash);
-    __shared__ int s_cnt;        // entries in ids[] / acc[]
-    __shared__ int s_next;       // position of the first unexpanded buffer entry (>= size: none)
-    __shared__ int s_best;       // upper layers: argmin slot
+// Read-only view of the graph in HBM (device_index.cuh).
+struct GraphView {
+    const float4 *vec;        // [n][d4]
+    const uint32_t *links0;   // [n][maxM0]
+    const uint32_t *up_base;  // [n]
+    const uint32_t *links_up; // [lists][maxM]
+    uint32_t d4, maxM, maxM0;
+    __device__ __forceinline__ const uint32_t *list(uint32_t node, int level) const {
+        return level == 0 ? links0 + (size_t)node * maxM0
+                          : links_up + ((size_t)__ldg(up_base + node) + (uint32_t)(level - 1)) * maxM;
+    }
+    __device__ __forceinline__ uint32_t list_len(int level) const { return level == 0 ? maxM0 : maxM; }
+};
 
+// Per-CTA scratch shared by the search and the construction kernels.
+struct TeamCtx {
+    uint64_t *buf_a, *buf_b, *acc;
+    uint32_t *ids;
+    float *dist;
+    uint32_t *hash;
+    int *s_cnt, *s_next, *s_best;
+    uint32_t hash_bits;
+};
+
+struct WorkCounters {
+    uint32_t D = 0, H0 = 0, Hup = 0, resets = 0;
+};
+
+// Greedy descent on one upper level (hnswalg.h:1278-1303 / :1216-1238): scan ALL neighbours of the current node,
+// move to the closest if it improves, repeat until no change.  argmin with lowest-slot tie-break equals the
+// reference's sequential strict '<' scan.
+template <int LPV, int CPL, int METRIC>
+__device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)[CPL], const GraphView &g, int level,
+                                             uint32_t &cur, float &curdist, WorkCounters &w) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int sub = tid % LPV, grp = tid / LPV;
-    const uint32_t qi = blockIdx.x;
-    const uint32_t ef = p.ef, d4 = p.d4;
-    const uint32_t HS = 1u << p.hash_bits;
-
-    // ---- stage the query (rows of Q are only 4-byte aligned when dim % 4 != 0) and clear the visited table ----
-    for (uint32_t i = tid; i < d4 * 4; i += kTeam) qs[i] = i < p.dim ? p.Q[(size_t)qi * p.dim + i] : 0.f;
-    for (uint32_t i = tid; i < HS; i += kTeam) hash[i] = kEmpty;
-    if (tid == 0) { s_cnt = 0; s_next = 0; }
-    __syncthreads();
-    float4 q[CPL];
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        __syncthreads();  // previous round's reads of ids/dist/s_best are done
+        const uint32_t *lst = g.list(cur, level);
+        int cnt = 0;  // lists are dense: valid slots are 0..cnt-1
+        for (uint32_t b0 = 0; b0 < g.maxM; b0 += kTeam) {
+            uint32_t nid = kEmpty;
+            if (b0 + tid < g.maxM) {
+                nid = __ldg(lst + b0 + tid);
+                c.ids[b0 + tid] = nid;
+            }
+            cnt += __syncthreads_count(nid != kEmpty);
+        }
+        eval_list<LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, cnt, c.dist, grp, sub);
+        __syncthreads();
+        w.D += cnt;
+        w.Hup += 1;
+        if (tid < 32) {
+            float bd = 3.402823466e+38f;
+            int bj = 0x7fffffff;
+            for (int j = lane; j < cnt; j += 32) {
+                const float dj = c.dist[j];
+                if (dj < bd) { bd = dj; bj = j; }
+            }
 #pragma unroll
-    for (int c = 0; c < CPL; c++) {
-        const uint32_t idx = sub + c * LPV;
-        q[c] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-    uint32_t wD = 0, wH0 = 0, wHup = 0, wReset = 0;  // work counters (meaningful in thread 0)
-
-    // ---- searchKnn prologue: distance to the entry point, greedy descent on levels maxlevel..1 ----
-    uint32_t cur = p.entry;
-    if (tid == 0) ids[0] = cur;
-    __syncthreads();
-    eval_list<LPV, CPL, METRIC>(q, p.vec, d4, ids, 1, dist, grp, sub);
-    __syncthreads();
-    float curdist = dist[0];
-    wD += 1;
-    for (int level = p.maxlevel; level > 0; --level) {
-        bool changed = true;
-        while (changed) {
-            changed = false;
-            __syncthreads();  // previous round's reads of ids/dist/s_best are done
-            const uint32_t base = __ldg(p.up_base + cur);
-            const uint32_t *lst = p.links_up + ((size_t)base + (uint32_t)(level - 1)) * p.maxM;
-            int cnt = 0;  // lists are dense: valid slots are 0..cnt-1
-            for (uint32_t b0 = 0; b0 < p.maxM; b0 += kTeam) {
-                uint32_t nid = kEmpty;
-                if (b0 + tid < p.maxM) {
-                    nid = __ldg(lst + b0 + tid);
-                    ids[b0 + tid] = nid;
-                }
-                cnt += __syncthreads_count(nid != kEmpty);
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
             }
-            eval_list<LPV, CPL, METRIC>(q, p.vec, d4, ids, cnt, dist, grp, sub);
-            __syncthreads();
-            wD += cnt;
-            wHup += 1;
-            if (tid < 32) {  // argmin, lowest slot wins ties (sequential strict '<' scan, hnswalg.h:1289-1300)
-                float bd = 3.402823466e+38f;
-                int bj = 0x7fffffff;
-                for (int j = lane; j < cnt; j += 32) {
-                    const float dj = dist[j];
-                    if (dj < bd) { bd = dj; bj = j; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-                    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                    if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
-                }
-                if (lane == 0) s_best = (cnt > 0 && bd < curdist) ? bj : -1;
-            }
-            __syncthreads();
-            const int b = s_best;
-            if (b >= 0) {
-                curdist = dist[b];
-                cur = ids[b];
-                changed = true;
-            }
+            if (lane == 0) *c.s_best = (cnt > 0 && bd < curdist) ? bj : -1;
+        }
+        __syncthreads();
+        const int b = *c.s_best;
+        if (b >= 0) {
+            curdist = c.dist[b];
+            cur = c.ids[b];
+            changed = true;
         }
     }
     __syncthreads();
+}
 
-    // ---- searchBaseLayerST: sorted top-ef buffer with expanded bits ----
-    int cb = 0;            // current buffer
-    int size = 1;          // entries in buf[cb]
+// Best-first beam search on one level (searchBaseLayerST<true>, hnswalg.h:309-440; the construction variant
+// searchBaseLayer :225-305 has the same result set when nothing is deleted): sorted top-ef buffer with expanded
+// bits, starting from (cur, curdist).  The visited table must be empty on entry.  On return the result is the
+// first `size` keys of (cb ? buf_b : buf_a), closest first.
+template <int LPV, int CPL, int METRIC>
+__device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[CPL], const GraphView &g, int level,
+                                           uint32_t ef, uint32_t cur, float curdist, int &cb, int &size,
+                                           WorkCounters &w) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sub = tid % LPV, grp = tid / LPV;
+    const uint32_t HS = 1u << c.hash_bits;
+    const uint32_t llen = g.list_len(level);
+    cb = 0;
+    size = 1;
     if (tid == 0) {
-        buf_a[0] = make_key(curdist, cur);
-        hash_insert(hash, p.hash_bits, cur);
-        s_next = 0;
+        c.buf_a[0] = make_key(curdist, cur);
+        hash_insert(c.hash, c.hash_bits, cur);
+        *c.s_next = 0;
     }
-    uint32_t hcount = 1;   // ids in the visited table (uniform across threads)
+    uint32_t hcount = 1;  // ids in the visited table (uniform across threads)
     __syncthreads();
 
     for (;;) {
-        const int next = s_next;
+        const int next = *c.s_next;
         if (next >= size) break;
-        uint64_t *src = cb ? buf_b : buf_a, *dst = cb ? buf_a : buf_b;
+        uint64_t *src = cb ? c.buf_b : c.buf_a, *dst = cb ? c.buf_a : c.buf_b;
         const uint32_t node = (uint32_t)src[next] & kIdMask;
-        const float bound = (uint32_t)size == ef ? ord2f((uint32_t)(src[ef - 1] >> 32)) : 3.402823466e+38f;
         const bool full = (uint32_t)size == ef;
+        const float bound = full ? ord2f((uint32_t)(src[ef - 1] >> 32)) : 3.402823466e+38f;
         __syncthreads();  // everyone has read s_next / src[next] before they are rewritten
         if (tid == 0) {
             src[next] |= (uint64_t)kExpanded;
-            s_cnt = 0;
-            s_next = 0x7fffffff;
+            *c.s_cnt = 0;
+            *c.s_next = 0x7fffffff;
         }
         // visited table at > 1/2 load: rebuild it from the buffer (results unchanged, see header)
         if (hcount > HS / 2) {
-            for (uint32_t i = tid; i < HS; i += kTeam) hash[i] = kEmpty;
+            for (uint32_t i = tid; i < HS; i += kTeam) c.hash[i] = kEmpty;
             __syncthreads();
-            for (int i = tid; i < size; i += kTeam) hash_insert(hash, p.hash_bits, (uint32_t)src[i] & kIdMask);
+            for (int i = tid; i < size; i += kTeam) hash_insert(c.hash, c.hash_bits, (uint32_t)src[i] & kIdMask);
             hcount = size;
-            wReset += 1;
+            w.resets += 1;
         }
         __syncthreads();
 
         // neighbour list of the expanded node -> unvisited ids, compacted into ids[]
-        for (uint32_t b0 = 0; b0 < p.maxM0; b0 += kTeam) {
+        const uint32_t *lst = g.list(node, level);
+        for (uint32_t b0 = 0; b0 < llen; b0 += kTeam) {
             uint32_t nid = kEmpty;
-            if (b0 + tid < p.maxM0) nid = __ldg(p.links0 + (size_t)node * p.maxM0 + b0 + tid);
+            if (b0 + tid < llen) nid = __ldg(lst + b0 + tid);
             bool isnew = false;
-            if (nid != kEmpty) isnew = hash_insert(hash, p.hash_bits, nid);
+            if (nid != kEmpty) isnew = hash_insert(c.hash, c.hash_bits, nid);
             const uint32_t m = __ballot_sync(0xffffffffu, isnew);
             int basepos = 0;
-            if (lane == 0 && m) basepos = atomicAdd(&s_cnt, __popc(m));
+            if (lane == 0 && m) basepos = atomicAdd(c.s_cnt, __popc(m));
             basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (isnew) ids[basepos + __popc(m & ((1u << lane) - 1u))] = nid;
+            if (isnew) c.ids[basepos + __popc(m & ((1u << lane) - 1u))] = nid;
         }
         __syncthreads();
-        const int nnew = s_cnt;
-        wH0 += 1;
-        wD += nnew;
+        const int nnew = *c.s_cnt;
+        w.H0 += 1;
+        w.D += nnew;
         hcount += nnew;
-        eval_list<LPV, CPL, METRIC>(q, p.vec, d4, ids, nnew, dist, grp, sub);
+        eval_list<LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, nnew, c.dist, grp, sub);
         __syncthreads();
-        if (tid == 0) s_cnt = 0;
+        if (tid == 0) *c.s_cnt = 0;
         __syncthreads();
         // admit against the pre-expansion bound (hnswalg.h:395: size < ef || lowerBound > dist)
         for (int b0 = 0; b0 < nnew; b0 += kTeam) {
             bool ok = false;
             uint64_t key = 0;
             if (b0 + tid < nnew) {
-                const float dj = dist[b0 + tid];
+                const float dj = c.dist[b0 + tid];
                 ok = !full || dj < bound;
-                key = make_key(dj, ids[b0 + tid]);
+                key = make_key(dj, c.ids[b0 + tid]);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, ok);
             int basepos = 0;
-            if (lane == 0 && m) basepos = atomicAdd(&s_cnt, __popc(m));
+            if (lane == 0 && m) basepos = atomicAdd(c.s_cnt, __popc(m));
             basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (ok) acc[basepos + __popc(m & ((1u << lane) - 1u))] = key;
+            if (ok) c.acc[basepos + __popc(m & ((1u << lane) - 1u))] = key;
         }
         __syncthreads();
-        const int m = s_cnt;
+        const int m = *c.s_cnt;
         int local_min = 0x7fffffff;
         if (m == 0) {
             // nothing admitted: buffer unchanged, find the next unexpanded entry after `next`
@@ -308,16 +311,16 @@ __global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) 
                 const uint64_t key = src[i];
                 const uint64_t km = key & kKeyMask;
                 int pos = i;
-                for (int j = 0; j < m; j++) pos += (acc[j] < km) ? 1 : 0;
+                for (int j = 0; j < m; j++) pos += (c.acc[j] < km) ? 1 : 0;
                 if ((uint32_t)pos < ef) {
                     dst[pos] = key;
                     if (!((uint32_t)key & kExpanded)) local_min = min(local_min, pos);
                 }
             }
             for (int j = kTeam - 1 - tid; j < m; j += kTeam) {
-                const uint64_t key = acc[j];
+                const uint64_t key = c.acc[j];
                 int r = 0;
-                for (int i = 0; i < m; i++) r += (acc[i] < key) ? 1 : 0;
+                for (int i = 0; i < m; i++) r += (c.acc[i] < key) ? 1 : 0;
                 int lo = 0, hi = size;  // upper bound: equal keys (impossible by construction) stay distinct
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
@@ -334,12 +337,65 @@ __global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));
-        if (lane == 0 && local_min != 0x7fffffff) atomicMin(&s_next, local_min);
+        if (lane == 0 && local_min != 0x7fffffff) atomicMin(c.s_next, local_min);
         __syncthreads();
     }
+}
+
+template <int LPV, int CPL, int METRIC>
+__global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
+    const SearchSmem L(p.ef, list_cap, p.d4, p.hash_bits);
+    __shared__ int s_ints[3];
+    TeamCtx c;
+    c.buf_a = (uint64_t *)(smem + L.off_buf0);
+    c.buf_b = (uint64_t *)(smem + L.off_buf1);
+    c.acc = (uint64_t *)(smem + L.off_acc);
+    c.ids = (uint32_t *)(smem + L.off_ids);
+    c.dist = (float *)(smem + L.off_dist);
+    c.hash = (uint32_t *)(smem + L.off_hash);
+    c.s_cnt = &s_ints[0]; c.s_next = &s_ints[1]; c.s_best = &s_ints[2];
+    c.hash_bits = p.hash_bits;
+    float *qs = (float *)(smem + L.off_q);
+    GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
+
+    const int tid = threadIdx.x;
+    const int sub = tid % LPV, grp = tid / LPV;
+    const uint32_t qi = blockIdx.x;
+    const uint32_t d4 = p.d4;
+    const uint32_t HS = 1u << p.hash_bits;
+
+    // ---- stage the query (rows of Q are only 4-byte aligned when dim % 4 != 0) and clear the visited table ----
+    for (uint32_t i = tid; i < d4 * 4; i += kTeam) qs[i] = i < p.dim ? p.Q[(size_t)qi * p.dim + i] : 0.f;
+    for (uint32_t i = tid; i < HS; i += kTeam) c.hash[i] = kEmpty;
+    if (tid == 0) { *c.s_cnt = 0; *c.s_next = 0; }
+    __syncthreads();
+    float4 q[CPL];
+#pragma unroll
+    for (int cc = 0; cc < CPL; cc++) {
+        const uint32_t idx = sub + cc * LPV;
+        q[cc] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    WorkCounters w;
+    // ---- searchKnn prologue: distance to the entry point, greedy descent on levels maxlevel..1 ----
+    uint32_t cur = p.entry;
+    if (tid == 0) c.ids[0] = cur;
+    __syncthreads();
+    eval_list<LPV, CPL, METRIC>(q, g.vec, d4, c.ids, 1, c.dist, grp, sub);
+    __syncthreads();
+    float curdist = c.dist[0];
+    w.D += 1;
+    for (int level = p.maxlevel; level > 0; --level) greedy_level<LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
+    __syncthreads();
+
+    // ---- searchBaseLayerST on level 0 ----
+    int cb, size;
+    beam_level<LPV, CPL, METRIC>(c, q, g, 0, p.ef, cur, curdist, cb, size, w);
 
     // ---- epilogue: first k entries are the result, closest first (hnswalg.h:1315-1322) ----
-    const uint64_t *res = cb ? buf_b : buf_a;
+    const uint64_t *res = cb ? c.buf_b : c.buf_a;
     for (uint32_t j = tid; j < p.k; j += kTeam) {
         uint64_t lab = 0xFFFFFFFFFFFFFFFFull;
         float dj = __int_as_float(0x7f800000);
@@ -354,8 +410,8 @@ __global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) 
     if (tid == 0) {
         if (p.out_counts) p.out_counts[qi] = min((uint32_t)size, p.k);
         if (p.out_work) {
-            uint32_t *w = p.out_work + (size_t)qi * 4;
-            w[0] = wD; w[1] = wH0; w[2] = wHup; w[3] = wReset;
+            uint32_t *wo = p.out_work + (size_t)qi * 4;
+            wo[0] = w.D; wo[1] = w.H0; wo[2] = w.Hup; wo[3] = w.resets;
         }
     }
 }

@@ -1,0 +1,104 @@
+"""GPU: batched addPoint graph construction (hnswalg.h:1153-1267 replaced by csrc/build.cu).
+
+The batched build cannot be bit-identical to serial insertion (points of one batch do not see each other), so the
+bars are: public fields identical to the reference for the same insertion order (they depend only on the level
+generator), graph invariants of checkIntegrity (hnswalg.h:1381-1410), a saved file the reference loads, and
+recall@10 within 1 pt of the CPU-built graph on the same data at the same ef."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import gauss
+from oracle import bind
+
+pytestmark = pytest.mark.gpu
+
+
+def _recall(labels, gt):
+    return float(np.mean([len(set(a) & set(b)) for a, b in zip(labels.tolist(), gt.tolist())]) / gt.shape[1])
+
+
+def _check_graph(idx, n, M):
+    lv = idx.element_levels_
+    inbound = np.zeros(n, np.int64)
+    for i in range(n):
+        for l in range(int(lv[i]) + 1):
+            nb = idx.get_linklist_at_level(i, l)
+            assert len(nb) <= (2 * M if l == 0 else M)
+            assert len(set(nb.tolist())) == len(nb), (i, l)           # no duplicates
+            assert (nb < n).all() and (nb != i).all(), (i, l)          # in range, no self link
+            assert (lv[nb] >= l).all(), (i, l)                         # hnswalg.h:547-548
+            if l == 0:
+                inbound[nb] += 1
+    assert (inbound[1:] > 0).all()                                      # hnswalg.h:1403
+
+
+@pytest.mark.parametrize("metric,n,d,M,efc", [(bind.L2, 6000, 32, 8, 60), (bind.IP, 5000, 48, 12, 80)])
+def test_fields_invariants_and_reference_loads_it(lib, orc, ref, tmp_path, metric, n, d, M, efc):
+    X = gauss(41, n, d)
+    if metric == bind.IP:
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+    Q = gauss(42, 300, d)
+    space = lib.L2Space(d) if metric == bind.L2 else lib.InnerProductSpace(d)
+    g = lib.HierarchicalNSW(space, n, M, efc)
+    g.addPoints(X[:1000])
+    for i in range(1000, 1010):            # the one-at-a-time pattern of build.cpp:137-145
+        g.addPoint(X[i], i)
+    g.addPoints(X[1010:], np.arange(1010, n, dtype=np.uint64))
+    c = orc.hnsw_new(metric, d, n, M, efc)
+    c.add(X)
+    ci = c.info()
+    # public fields depend only on the level generator (hnswalg.h:207-211,1187-1198,1255-1265): identical
+    assert g.cur_element_count == n == ci["cur_element_count"]
+    assert g.maxlevel_ == ci["maxlevel"] and g.enterpoint_node_ == ci["enterpoint"]
+    assert np.array_equal(g.element_levels_, c.levels())
+    _check_graph(g, n, M)
+    # saveIndex output: the reference's own loader accepts it (integrity walk, hnswalg.h:754-770) and searches it
+    path = str(tmp_path / "gpu_built.bin")
+    g.saveIndex(path)
+    assert os.path.getsize(path) == g.indexFileSize()
+    back = (ref.hnsw_load(metric, d, path) if ref is not None else orc.hnsw_load(metric, d, path))
+    bf = orc.bf_new(metric, d, n)
+    bf.add(X)
+    gt = bf.search(Q, 10)["labels"]
+    rec_ref_on_gpu_graph = _recall(back.search(Q, 10, 64)["labels"], gt)
+    rec_gpu = _recall(g.searchKnnBatch(Q, 10, ef=64)["labels"], gt)
+    rec_cpu = _recall(c.search(Q, 10, 64)["labels"], gt)
+    assert abs(rec_ref_on_gpu_graph - rec_gpu) <= 0.005            # same graph, both engines
+    assert rec_gpu >= rec_cpu - 0.01, (rec_gpu, rec_cpu)            # GPU-built graph is as good as the CPU-built one
+
+
+def test_lowrank_recall_and_interleaved_search(lib, orc):
+    n, d, M, efc = 20000, 64, 16, 100
+    X = bind.lowrank_data(n, d, seed=3)
+    Q = bind.lowrank_data(400, d, seed=4)
+    g = lib.HierarchicalNSW(lib.L2Space(d), n, M, efc)
+    g.addPoints(X[:5000])
+    r0 = g.searchKnnBatch(X[:50], 1, ef=32)                     # search between insertions: flushes the staged points
+    assert (r0["labels"][:, 0] == np.arange(50)).mean() >= 0.98
+    g.addPoints(X[5000:])
+    bf = lib.BruteforceSearch(lib.L2Space(d), n)
+    bf.addPoints(X)
+    gt = bf.searchKnnBatch(Q, 10)["labels"]
+    c = orc.hnsw_new(bind.L2, d, n, M, efc)
+    c.add(X)
+    for ef in (16, 64):
+        rg = _recall(g.searchKnnBatch(Q, 10, ef=ef)["labels"], gt)
+        rc = _recall(c.search(Q, 10, ef)["labels"], gt)
+        assert rg >= rc - 0.01, (ef, rg, rc)
+    st = g.stats()
+    assert st["kernel_launches"] > 0
+
+
+def test_capacity_and_duplicate_label(lib):
+    g = lib.HierarchicalNSW(lib.L2Space(8), 10, 4, 20)
+    g.addPoints(gauss(1, 10, 8))
+    with pytest.raises(lib.B200Error, match="exceeds the specified limit"):
+        g.addPoint(np.zeros(8, np.float32), 99)
+    g2 = lib.HierarchicalNSW(lib.L2Space(8), 10, 4, 20)
+    g2.addPoint(np.zeros(8, np.float32), 5)
+    with pytest.raises(lib.B200Error):
+        g2.addPoint(np.ones(8, np.float32), 5)
+    r = g.searchKnnBatch(gauss(1, 10, 8), 3, ef=10)
+    assert (r["labels"][:, 0] == np.arange(10)).all()
