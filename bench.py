@@ -120,7 +120,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def result(self):
         self.stop_flag = True
@@ -227,17 +227,31 @@ def run_b200(a, rank, local_rank, world):
     threads = max(1, (os.cpu_count() or 1) // world)
     X = shard_data(a, rank)
     batches = query_batches(a)
-    path, build_s = build_graph_with_reference(a, rank, X, threads)
-    t0 = time.time()
-    idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), path, device=local_rank)
-    load_s = time.time() - t0
+    shard_labels = np.arange(a.n, dtype=np.uint64) + np.uint64(rank * a.n)
+    if world == 1:
+        # the graph both arms search: built by the reference on the host cores, loaded from its saveIndex file
+        path, build_s = build_graph_with_reference(a, rank, X, threads)
+        t0 = time.time()
+        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), path, device=local_rank)
+        load_s = time.time() - t0
+        graph_note = "reference-built saveIndex file%s, loaded in %.1f s" % (
+            "" if build_s == 0 else " (%.1f s, %.0f points/s on %d threads)" % (build_s, a.n / build_s, threads), load_s)
+    else:
+        # one sub-index per GPU, built on that GPU (batched addPoint, csrc/build.cu)
+        path = None
+        t0 = time.time()
+        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), a.n, a.M, a.efc, device=local_rank)
+        idx.addPoints(X, shard_labels)
+        idx.flush()
+        build_s = time.time() - t0
+        graph_note = "per-GPU shard graph built on the GPU in %.1f s (%.0f points/s)" % (build_s, a.n / build_s)
 
     # exact ground truth for the first 1000 queries from the exact-scan kernel (global over all shards when N > 1)
     Qs = batches[0][:1000]
     bf = pkg.BruteforceSearch(pkg.L2Space(a.dim), a.n, device=local_rank)
-    bf.addPoints(X, np.arange(a.n, dtype=np.uint64) + np.uint64(rank * a.n))
+    bf.addPoints(X, shard_labels)
     g = bf.searchKnnBatch(Qs, a.k)
-    del bf, X
+    del bf
     stream = torch.cuda.current_stream().cuda_stream
 
     def merged(labels_t, dists_t, nq):
@@ -340,6 +354,25 @@ def run_b200(a, rank, local_rank, world):
     h2d = a.nq * a.dim * 4
     d2h = a.nq * a.k * 12 + a.nq * 4 + a.nq * 16
 
+    # ---- C5: batched GPU graph build of the same points (wall clock incl. H2D; not part of the timed search region)
+    build_info = None
+    if rank == 0 and world == 1 and not os.environ.get("B200HNSW_BENCH_SKIP_BUILD"):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gi = pkg.HierarchicalNSW(pkg.L2Space(a.dim), a.n, a.M, a.efc, device=local_rank)
+        gi.addPoints(X, shard_labels)
+        gi.flush()
+        gsec = time.perf_counter() - t0
+        gst = gi.stats()
+        rg = gi.searchKnnBatch(Qs, a.k, ef=ef)["labels"]
+        build_info = {"gpu_points_per_s": a.n / gsec, "gpu_seconds": gsec, "gpu_kernel_ms": gst["last_kernel_ms"],
+                      "dist_evals_per_point": gst["dist_evals"] / a.n,
+                      "recall_at_10_gpu_built_graph": round(recall_at_k(rg, gt), 4),
+                      "recall_at_10_reference_built_graph": round(rec, 4), "ef": ef,
+                      "reference_points_per_s": (a.n / build_s) if build_s else None, "reference_threads": threads}
+        del gi
+    del X
+
     if rank == 0:
         bytes_sum = [algorithmic_bytes(a, w) for w in works]
         per_launch = float(np.mean([b[0] for b in bytes_sum]))
@@ -353,11 +386,13 @@ def run_b200(a, rank, local_rank, world):
             except Exception:
                 traffic = None
         resets = int(sum(w[:, 3].sum() for w in works))
-        cpu_leg = None
-        try:
-            cpu_leg, _ = cpu_reference_leg(a, path, batches, ef, a.cpu_seconds, os.cpu_count() or 1)
-        except Exception as e:  # the checker binary is missing: report it, never substitute
-            cpu_leg = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+        cpu_leg = None  # measured on rank 0 at N = 1 only
+        if world == 1:
+            try:
+                cpu_leg, _ = cpu_reference_leg(a, path, batches, ef, a.cpu_seconds, os.cpu_count() or 1)
+            except Exception as e:  # the checker binary is missing: report it, never substitute
+                cpu_leg = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference",
+                           "sample": "unavailable: %s" % e}
         line = {
             "metric": "QPS @ recall@10>=0.95, 1Mx128 L2", "value": world * a.nq * a.steps / (ms_total * 1e-3),
             "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -369,9 +404,7 @@ def run_b200(a, rank, local_rank, world):
                        "counts shard-level searches (merged queries/s = value/%d)" % (world, a.n, world),
                        "l2_policy": "inputs larger than L2 (index %.0f MB vs 126 MB L2); %d distinct query batches cycled"
                                     % ((a.n * (a.dim * 4 + 8 * a.M)) / 1e6, len(batches)),
-                       "graph": "reference-built saveIndex file%s, loaded in %.1f s" %
-                                ("" if build_s == 0 else " (%.1f s, %.0f points/s on %d threads)" % (build_s, a.n / build_s, threads),
-                                 load_s),
+                       "graph": graph_note, "build": build_info,
                        "visited_table_rebuilds_per_batch": resets / len(works)},
             "clocks": clocks,
             "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,

@@ -10,7 +10,7 @@
 //
 // Batching.  The reference inserts one point at a time; here points are linked in insertion order in batches that
 // see the graph as of the start of their batch.  A batch is never larger than (linked points) / build_ratio, so at
-// most a 1/build_ratio fraction of a point's true neighbours is invisible to it, and a point that raises the
+// most a 1/build_ratio (default 1/32) fraction of a point's true neighbours is invisible to it, and a point that raises the
 // maximum level always ends its batch (it becomes the entry point of everything after it, :1262-1265).  Levels,
 // element count, entry point and max level are assigned at add time with the reference's generator and are
 // bit-identical to the reference for the same insertion order (:207-211,1187-1198).
@@ -400,7 +400,7 @@ int HnswIndex::flush() {
     B200_CUDA_OK(cudaSetDevice(dev.device));
     const size_t n_new = m.cur - linked;
     const size_t rec = m.size_data;
-    const size_t build_ratio = env_size("B200HNSW_BUILD_RATIO", 8);
+    const size_t build_ratio = env_size("B200HNSW_BUILD_RATIO", 32);
     const size_t max_batch = env_size("B200HNSW_BUILD_BATCH", 16384);
 
     // ---- upload vectors + labels of the staged points (records carry empty lists) ----
