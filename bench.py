@@ -254,17 +254,13 @@ def run_b200(a, rank, local_rank, world):
     del bf
     stream = torch.cuda.current_stream().cuda_stream
 
+    from research_new_hnsw_b200.sharded import ShardedSearcher, cuda_merge
+    sharded = ShardedSearcher(None, cuda_merge(lambda: stream), device=dev)
+
     def merged(labels_t, dists_t, nq):
         """all_gather per-shard rows + GPU k-way merge; identity at world == 1."""
-        if world == 1:
-            return labels_t, dists_t
-        gl = torch.empty((world,) + tuple(labels_t.shape), dtype=torch.int64, device=dev)
-        gd = torch.empty((world,) + tuple(dists_t.shape), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(gl, labels_t)
-        dist.all_gather_into_tensor(gd, dists_t)
-        ol, od = torch.empty_like(labels_t), torch.empty_like(dists_t)
-        pkg.merge_topk_device(gl.data_ptr(), gd.data_ptr(), world, nq, a.k, ol.data_ptr(), od.data_ptr(), stream)
-        return ol, od
+        sharded.local_search = lambda Q, k: (labels_t, dists_t)
+        return sharded.search(None, a.k)
 
     gt_l = torch.from_numpy(g["labels"].view(np.int64)).to(dev)
     gt_d = torch.from_numpy(g["dists"]).to(dev)

@@ -28,6 +28,7 @@
 
 namespace b200 {
 
+constexpr int kTeam = 128;      // threads per CTA of the build kernels
 constexpr uint32_t kCapIn = 32;  // incoming reverse edges kept per list and batch
 
 struct BuildArgs {
@@ -63,16 +64,9 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
     const SearchSmem L(p.efc, list_cap, p.d4, p.hash_bits);
-    __shared__ int s_ints[3];
+    __shared__ int s_ints[kTeamInts];
     TeamCtx c;
-    c.buf_a = (uint64_t *)(smem + L.off_buf0);
-    c.buf_b = (uint64_t *)(smem + L.off_buf1);
-    c.acc = (uint64_t *)(smem + L.off_acc);
-    c.ids = (uint32_t *)(smem + L.off_ids);
-    c.dist = (float *)(smem + L.off_dist);
-    c.hash = (uint32_t *)(smem + L.off_hash);
-    c.s_cnt = &s_ints[0]; c.s_next = &s_ints[1]; c.s_best = &s_ints[2];
-    c.hash_bits = p.hash_bits;
+    c.bind(smem, L, s_ints, p.hash_bits);
     GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
 
     const int tid = threadIdx.x;
@@ -83,22 +77,22 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
 
     float4 q[CPL];
     load_row<LPV, CPL>(q, p.vec + (size_t)pid * p.d4, p.d4, sub);
-    if (tid == 0) { *c.s_cnt = 0; *c.s_next = 0; c.ids[0] = p.entry; }
+    if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; *c.s_next = 0; c.ids[0] = p.entry; }
     __syncthreads();
     WorkCounters w;
     uint32_t cur = p.entry;
-    eval_list<LPV, CPL, METRIC>(q, g.vec, p.d4, c.ids, 1, c.dist, grp, sub);
+    eval_list<kTeam, LPV, CPL, METRIC>(q, g.vec, p.d4, c.ids, 1, c.dist, grp, sub);
     __syncthreads();
     float curdist = c.dist[0];
     w.D += 1;
-    for (int level = p.maxlevel; level > plevel; --level) greedy_level<LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
+    for (int level = p.maxlevel; level > plevel; --level) greedy_level<kTeam, LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
     const uint32_t slot0 = p.list_off[blockIdx.x];
     for (int level = min(plevel, p.maxlevel); level >= 0; --level) {
         __syncthreads();
         for (uint32_t i = tid; i < HS; i += kTeam) c.hash[i] = kEmpty;
         __syncthreads();
         int cb, size;
-        beam_level<LPV, CPL, METRIC>(c, q, g, level, p.efc, cur, curdist, cb, size, w);
+        beam_level<kTeam, LPV, CPL, METRIC>(c, q, g, level, p.efc, cur, curdist, cb, size, w);
         const uint64_t *res = cb ? c.buf_b : c.buf_a;
         uint64_t *out = p.cand + (size_t)(slot0 + level) * p.efc;
         for (int j = tid; j < size; j += kTeam) out[j] = res[j] & kKeyMask;
@@ -135,7 +129,7 @@ __device__ __forceinline__ int heuristic_prune(const GraphView &g, const uint64_
         const uint64_t key = cand[ci];
         const float dq = ord2f((uint32_t)(key >> 32));
         if (ci + 1 < n) load_row<LPV, CPL>(vn, g.vec + (size_t)((uint32_t)cand[ci + 1] & kIdMask) * g.d4, g.d4, sub);
-        eval_list<LPV, CPL, METRIC, true>(v, g.vec, g.d4, ids, ns, dist, grp, sub);
+        eval_list<kTeam, LPV, CPL, METRIC, true>(v, g.vec, g.d4, ids, ns, dist, grp, sub);
         evals += ns;
         __syncthreads();
         bool bad = false;
@@ -248,7 +242,7 @@ __global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p,
     // full: candidates = existing (distances to this node evaluated now, :597-601) + incoming
     float4 q[CPL];
     load_row<LPV, CPL>(q, p.vec + (size_t)node * p.d4, p.d4, sub);
-    eval_list<LPV, CPL, METRIC>(q, g.vec, p.d4, ids, deg, dist, grp, sub);
+    eval_list<kTeam, LPV, CPL, METRIC>(q, g.vec, p.d4, ids, deg, dist, grp, sub);
     __syncthreads();
     for (int j = tid; j < deg; j += kTeam) raw[j] = make_key(dist[j], ids[j]);
     __syncthreads();

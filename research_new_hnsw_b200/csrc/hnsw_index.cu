@@ -162,13 +162,14 @@ int HnswIndex::ensure_scratch(size_t nq, size_t k) {
     return 0;
 }
 
-// Visited-table size: large enough that a typical query at this ef never rebuilds it (D ~ 30*ef + 500 on the
-// 1M x 128, M=32 graph), bounded so several CTAs still fit in an SM's 228 KB.
-uint32_t pick_hash_bits(size_t ef, size_t list_cap) {
+// Visited-table size.  128-thread teams (8 resident queries per SM): large enough that a typical query at this ef
+// never rebuilds it (D ~ 30*ef + 500 on the 1M x 128, M=32 graph).  Smaller teams trade table
+// size for resident queries: the table is rebuilt from the buffer at 5/8 load (re-evaluations only).
+uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
+    const size_t need = 2 * (ef + list_cap);
     if (const char *e = getenv("B200HNSW_HASH_BITS")) {
         const int b = atoi(e);
         if (b >= 8 && b <= 15) {
-            size_t need = 2 * (ef + list_cap);
             uint32_t bits = (uint32_t)b;
             while ((1ull << bits) < need) bits++;
             return bits;
@@ -176,48 +177,65 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap) {
     }
     size_t want = 64 * ef + 1024;
     if (want > 16384) want = 16384;
-    const size_t need = 2 * (ef + list_cap);
+    if (team == 64) want /= 2;
+    if (team == 32) want /= 4;
     if (want < need) want = need;
     uint32_t bits = 10;
     while ((1ull << bits) < want) bits++;
     return bits;
 }
 
-template <int LPV, int CPL, int METRIC>
+template <int TEAM, int LPV, int CPL, int METRIC>
 static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
     static bool configured[16] = {};  // per device; set once (benign race: idempotent)
     int d = 0;
     cudaGetDevice(&d);
     if (d < 16 && !configured[d]) {
         cudaFuncAttributes fa;
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<LPV, CPL, METRIC>));
+        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC>));
         int optin = 0;
         B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<LPV, CPL, METRIC>,
+        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
-    hnsw_search_kernel<LPV, CPL, METRIC><<<a.nq, kTeam, smem, st>>>(a);
+    hnsw_search_kernel<TEAM, LPV, CPL, METRIC><<<a.nq, TEAM, smem, st>>>(a);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int METRIC>
-static int launch_metric(const SearchArgs &a, size_t smem, cudaStream_t st) {
+template <int TEAM, int METRIC>
+static int launch_team(const SearchArgs &a, size_t smem, cudaStream_t st) {
     const uint32_t d4 = a.d4;
-    if (d4 <= 8) return launch_one<8, 1, METRIC>(a, smem, st);
-    if (d4 <= 16) return launch_one<8, 2, METRIC>(a, smem, st);
-    if (d4 <= 24) return launch_one<8, 3, METRIC>(a, smem, st);
-    if (d4 <= 32) return launch_one<8, 4, METRIC>(a, smem, st);
-    if (d4 <= 48) return launch_one<16, 3, METRIC>(a, smem, st);
-    if (d4 <= 64) return launch_one<16, 4, METRIC>(a, smem, st);
-    if (d4 <= 96) return launch_one<32, 3, METRIC>(a, smem, st);
-    if (d4 <= 128) return launch_one<32, 4, METRIC>(a, smem, st);
-    if (d4 <= 192) return launch_one<32, 6, METRIC>(a, smem, st);
-    if (d4 <= 256) return launch_one<32, 8, METRIC>(a, smem, st);
+    if (d4 <= 8) return launch_one<TEAM, 8, 1, METRIC>(a, smem, st);
+    if (d4 <= 16) return launch_one<TEAM, 8, 2, METRIC>(a, smem, st);
+    if (d4 <= 24) return launch_one<TEAM, 8, 3, METRIC>(a, smem, st);
+    if (d4 <= 32) return launch_one<TEAM, 8, 4, METRIC>(a, smem, st);
+    if (d4 <= 48) return launch_one<TEAM, 16, 3, METRIC>(a, smem, st);
+    if (d4 <= 64) return launch_one<TEAM, 16, 4, METRIC>(a, smem, st);
+    if (d4 <= 96) return launch_one<TEAM, 32, 3, METRIC>(a, smem, st);
+    if (d4 <= 128) return launch_one<TEAM, 32, 4, METRIC>(a, smem, st);
+    if (d4 <= 192) return launch_one<TEAM, 32, 6, METRIC>(a, smem, st);
+    if (d4 <= 256) return launch_one<TEAM, 32, 8, METRIC>(a, smem, st);
     set_error("dimension > 1024 is not supported by the search kernel");
     return B200HNSW_E_UNSUPPORTED;
+}
+
+template <int METRIC>
+static int launch_metric(const SearchArgs &a, size_t smem, int team, cudaStream_t st) {
+    if (team == 32) return launch_team<32, METRIC>(a, smem, st);
+    if (team == 64) return launch_team<64, METRIC>(a, smem, st);
+    return launch_team<128, METRIC>(a, smem, st);
+}
+
+// Team size: a batch that cannot fill the GPU with 64-thread teams is latency-bound -> 128 threads per query.
+int pick_team(size_t nq) {
+    if (const char *e = getenv("B200HNSW_TEAM")) {
+        const int t = atoi(e);
+        if (t == 32 || t == 64 || t == 128) return t;
+    }
+    return nq >= 148 * 16 ? 64 : 128;
 }
 
 int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd,
@@ -250,14 +268,15 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.n = (uint32_t)linked; a.entry = dev_entry; a.maxlevel = dev_maxlevel;
     a.dim = (uint32_t)host.dim; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)host.maxM; a.maxM0 = (uint32_t)host.maxM0;
     a.nq = (uint32_t)nq; a.k = (uint32_t)k; a.ef = (uint32_t)efx;
-    a.hash_bits = pick_hash_bits(efx, list_cap);
+    const int team = pick_team(nq);
+    a.hash_bits = pick_hash_bits(efx, list_cap, team);
     const SearchSmem L(a.ef, (uint32_t)list_cap, a.d4, a.hash_bits);
     if (L.total > 226 * 1024) {
         set_error("search configuration needs more than 226 KB of shared memory");
         return B200HNSW_E_UNSUPPORTED;
     }
     stats.kernel_launches += 1;
-    return prm.metric == B200HNSW_L2 ? launch_metric<0>(a, L.total, st) : launch_metric<1>(a, L.total, st);
+    return prm.metric == B200HNSW_L2 ? launch_metric<0>(a, L.total, team, st) : launch_metric<1>(a, L.total, team, st);
 }
 
 __global__ void fill_pad_kernel(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k) {

@@ -59,7 +59,8 @@ struct HnswIndex {
     int sync_host_mirror();
 };
 
-uint32_t pick_hash_bits(size_t ef, size_t list_cap);
+uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team = 128);
+int pick_team(size_t nq);
 void fill_pad_rows(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k, cudaStream_t st);
 
 }  // namespace b200

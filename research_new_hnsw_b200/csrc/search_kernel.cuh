@@ -26,7 +26,9 @@
 
 namespace b200 {
 
-constexpr int kTeam = 128;  // threads per query
+// Threads per query ("team" = one CTA).  128 gives the shortest per-query latency (32 vectors in flight per hop);
+// 64 doubles the number of resident queries per SM and wins on throughput for large batches.
+constexpr int kTeamMax = 128;
 
 struct SearchArgs {
     const float4 *vec;        // [n][d4]
@@ -48,7 +50,7 @@ struct SearchArgs {
 
 // shared-memory carve-up, shared by host (size) and device (pointers)
 struct SearchSmem {
-    uint32_t off_buf0, off_buf1, off_acc, off_ids, off_dist, off_q, off_hash, total;
+    uint32_t off_buf0, off_buf1, off_acc, off_ids, off_dist, off_pref, off_q, off_hash, total;
     __host__ __device__ SearchSmem(uint32_t ef, uint32_t list_cap, uint32_t d4, uint32_t hash_bits) {
         uint32_t o = 0;
         off_buf0 = o; o += ef * 8;
@@ -56,6 +58,7 @@ struct SearchSmem {
         off_acc = o;  o += list_cap * 8;
         off_ids = o;  o += list_cap * 4;
         off_dist = o; o += list_cap * 4;
+        off_pref = o; o += list_cap * 4;
         o = (o + 15) & ~15u;
         off_q = o;    o += d4 * 16;
         off_hash = o; o += (1u << hash_bits) * 4;
@@ -72,23 +75,40 @@ __device__ __forceinline__ float group_sum(float v, uint32_t gmask) {
     return v;
 }
 
+// One 128-bit chunk of the distance sum on sm_100a's packed fp32 pipe (FFMA2: two fused multiply-adds per
+// instruction): L2 -> diff = fma(v, -1, q), acc = fma(diff, diff, acc); IP -> acc = fma(q, v, acc).  The two halves
+// of the accumulator are added once per vector.
 template <int METRIC>
-__device__ __forceinline__ float acc4(float acc, const float4 &q, const float4 &v) {
+__device__ __forceinline__ float2 acc4(float2 acc, const float4 &q, const float4 &v) {
+#ifdef B200_NO_FFMA2
     if (METRIC == 0) {
         float a = q.x - v.x, b = q.y - v.y, c = q.z - v.z, d = q.w - v.w;
-        acc = fmaf(a, a, acc); acc = fmaf(b, b, acc); acc = fmaf(c, c, acc); acc = fmaf(d, d, acc);
+        acc.x = fmaf(a, a, acc.x); acc.y = fmaf(b, b, acc.y); acc.x = fmaf(c, c, acc.x); acc.y = fmaf(d, d, acc.y);
     } else {
-        acc = fmaf(q.x, v.x, acc); acc = fmaf(q.y, v.y, acc); acc = fmaf(q.z, v.z, acc); acc = fmaf(q.w, v.w, acc);
+        acc.x = fmaf(q.x, v.x, acc.x); acc.y = fmaf(q.y, v.y, acc.y);
+        acc.x = fmaf(q.z, v.z, acc.x); acc.y = fmaf(q.w, v.w, acc.y);
+    }
+    return acc;
+#endif
+    if (METRIC == 0) {
+        const float2 m1 = make_float2(-1.f, -1.f);
+        const float2 d0 = __ffma2_rn(make_float2(v.x, v.y), m1, make_float2(q.x, q.y));
+        const float2 d1 = __ffma2_rn(make_float2(v.z, v.w), m1, make_float2(q.z, q.w));
+        acc = __ffma2_rn(d0, d0, acc);
+        acc = __ffma2_rn(d1, d1, acc);
+    } else {
+        acc = __ffma2_rn(make_float2(q.x, q.y), make_float2(v.x, v.y), acc);
+        acc = __ffma2_rn(make_float2(q.z, q.w), make_float2(v.z, v.w), acc);
     }
     return acc;
 }
 
 // Distances from the query (register slices q[]) to ids[0..n): each group of LPV lanes owns one vector at a time,
 // two vectors (2*CPL 128-bit loads per lane) are in flight per group.  dists[j] is written by the group leader.
-template <int LPV, int CPL, int METRIC, bool CACHED = false>
+template <int TEAM, int LPV, int CPL, int METRIC, bool CACHED = false>
 __device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *__restrict__ vec, uint32_t d4,
                                           const uint32_t *ids, int n, float *dists, int grp, int sub) {
-    constexpr int NGRP = kTeam / LPV;
+    constexpr int NGRP = TEAM / LPV;
     const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
     for (int j = grp; j < n; j += 2 * NGRP) {
         const int j2 = j + NGRP;
@@ -106,21 +126,66 @@ __device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *
             const uint32_t idx = sub + c * LPV;
             vb[c] = (has2 && idx < d4) ? (CACHED ? __ldg(rb + idx) : ldg_stream(rb + idx)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float sa = 0.f, sb = 0.f;
+        float2 pa = make_float2(0.f, 0.f), pb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
             const uint32_t idx = sub + c * LPV;
             if (idx < d4) {
-                sa = acc4<METRIC>(sa, q[c], va[c]);
-                sb = acc4<METRIC>(sb, q[c], vb[c]);
+                pa = acc4<METRIC>(pa, q[c], va[c]);
+                pb = acc4<METRIC>(pb, q[c], vb[c]);
             }
         }
-        sa = group_sum<LPV>(sa, gmask);
-        sb = group_sum<LPV>(sb, gmask);
+        float sa = group_sum<LPV>(pa.x + pa.y, gmask);
+        float sb = group_sum<LPV>(pb.x + pb.y, gmask);
         if (METRIC == 1) { sa = 1.0f - sa; sb = 1.0f - sb; }
         if (sub == 0) {
             dists[j] = sa;
             if (has2) dists[j2] = sb;
+        }
+    }
+}
+
+// Same gather as eval_list, fused with the admission test of searchBaseLayerST (hnswalg.h:395: size < ef ||
+// lowerBound > dist): the group leader appends the key of an admitted neighbour to acc[] (order irrelevant, the merge
+// ranks keys).
+template <int TEAM, int LPV, int CPL, int METRIC>
+__device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 *__restrict__ vec, uint32_t d4,
+                                           const uint32_t *ids, int n, bool full, float bound, uint64_t *acc,
+                                           int *s_acc, int grp, int sub) {
+    constexpr int NGRP = TEAM / LPV;
+    const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
+    for (int j = grp; j < n; j += 2 * NGRP) {
+        const int j2 = j + NGRP;
+        const bool has2 = j2 < n;
+        const uint32_t ida = ids[j], idb = ids[has2 ? j2 : j];
+        const float4 *ra = vec + (size_t)ida * d4;
+        const float4 *rb = vec + (size_t)idb * d4;
+        float4 va[CPL], vb[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = sub + c * LPV;
+            va[c] = idx < d4 ? ldg_stream(ra + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = sub + c * LPV;
+            vb[c] = (has2 && idx < d4) ? ldg_stream(rb + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float2 pa = make_float2(0.f, 0.f), pb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = sub + c * LPV;
+            if (idx < d4) {
+                pa = acc4<METRIC>(pa, q[c], va[c]);
+                pb = acc4<METRIC>(pb, q[c], vb[c]);
+            }
+        }
+        float sa = group_sum<LPV>(pa.x + pa.y, gmask);
+        float sb = group_sum<LPV>(pb.x + pb.y, gmask);
+        if (METRIC == 1) { sa = 1.0f - sa; sb = 1.0f - sb; }
+        if (sub == 0) {
+            if (!full || sa < bound) acc[atomicAdd(s_acc, 1)] = make_key(sa, ida);
+            if (has2 && (!full || sb < bound)) acc[atomicAdd(s_acc, 1)] = make_key(sb, idb);
         }
     }
 }
@@ -155,10 +220,24 @@ struct TeamCtx {
     uint64_t *buf_a, *buf_b, *acc;
     uint32_t *ids;
     float *dist;
+    uint32_t *pref;   // neighbour list prefetched for the predicted next expansion
     uint32_t *hash;
-    int *s_cnt, *s_next, *s_best;
+    int *s_cnt, *s_next, *s_best, *s_acc, *s_pref;
     uint32_t hash_bits;
+    template <class Smem>
+    __device__ __forceinline__ void bind(unsigned char *smem, const Smem &L, int *ints, uint32_t bits) {
+        buf_a = (uint64_t *)(smem + L.off_buf0);
+        buf_b = (uint64_t *)(smem + L.off_buf1);
+        acc = (uint64_t *)(smem + L.off_acc);
+        ids = (uint32_t *)(smem + L.off_ids);
+        dist = (float *)(smem + L.off_dist);
+        pref = (uint32_t *)(smem + L.off_pref);
+        hash = (uint32_t *)(smem + L.off_hash);
+        s_cnt = ints; s_next = ints + 1; s_best = ints + 2; s_acc = ints + 3; s_pref = ints + 4;
+        hash_bits = bits;
+    }
 };
+constexpr int kTeamInts = 5;
 
 struct WorkCounters {
     uint32_t D = 0, H0 = 0, Hup = 0, resets = 0;
@@ -167,7 +246,7 @@ struct WorkCounters {
 // Greedy descent on one upper level (hnswalg.h:1278-1303 / :1216-1238): scan ALL neighbours of the current node,
 // move to the closest if it improves, repeat until no change.  argmin with lowest-slot tie-break equals the
 // reference's sequential strict '<' scan.
-template <int LPV, int CPL, int METRIC>
+template <int TEAM, int LPV, int CPL, int METRIC>
 __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)[CPL], const GraphView &g, int level,
                                              uint32_t &cur, float &curdist, WorkCounters &w) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -178,7 +257,7 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
         __syncthreads();  // previous round's reads of ids/dist/s_best are done
         const uint32_t *lst = g.list(cur, level);
         int cnt = 0;  // lists are dense: valid slots are 0..cnt-1
-        for (uint32_t b0 = 0; b0 < g.maxM; b0 += kTeam) {
+        for (uint32_t b0 = 0; b0 < g.maxM; b0 += TEAM) {
             uint32_t nid = kEmpty;
             if (b0 + tid < g.maxM) {
                 nid = __ldg(lst + b0 + tid);
@@ -186,7 +265,7 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
             }
             cnt += __syncthreads_count(nid != kEmpty);
         }
-        eval_list<LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, cnt, c.dist, grp, sub);
+        eval_list<TEAM, LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, cnt, c.dist, grp, sub);
         __syncthreads();
         w.D += cnt;
         w.Hup += 1;
@@ -220,22 +299,29 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
 // searchBaseLayer :225-305 has the same result set when nothing is deleted): sorted top-ef buffer with expanded
 // bits, starting from (cur, curdist).  The visited table must be empty on entry.  On return the result is the
 // first `size` keys of (cb ? buf_b : buf_a), closest first.
-template <int LPV, int CPL, int METRIC>
+//
+// Per hop (4 block barriers): [list of the node to expand: from the prefetch buffer when the prediction was right,
+// else one coalesced global read] -> visited filter + compaction -> gather + distance + admission (eval_admit)
+// while the last warp prefetches the list of the best other unexpanded entry -> rank merge.
+template <int TEAM, int LPV, int CPL, int METRIC>
 __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[CPL], const GraphView &g, int level,
                                            uint32_t ef, uint32_t cur, float curdist, int &cb, int &size,
                                            WorkCounters &w) {
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = tid % LPV, grp = tid / LPV;
     const uint32_t HS = 1u << c.hash_bits;
     const uint32_t llen = g.list_len(level);
+    const bool can_pref = llen <= 64;  // the prefetching warp holds the list in two registers per lane
     cb = 0;
     size = 1;
     if (tid == 0) {
         c.buf_a[0] = make_key(curdist, cur);
         hash_insert(c.hash, c.hash_bits, cur);
         *c.s_next = 0;
+        *c.s_pref = -1;
     }
-    uint32_t hcount = 1;  // ids in the visited table (uniform across threads)
+    uint32_t hcount = 1;      // ids in the visited table (uniform across threads)
+    uint32_t pref_node = kEmpty;  // node whose list sits in c.pref[] (uniform)
     __syncthreads();
 
     for (;;) {
@@ -245,27 +331,32 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
         const uint32_t node = (uint32_t)src[next] & kIdMask;
         const bool full = (uint32_t)size == ef;
         const float bound = full ? ord2f((uint32_t)(src[ef - 1] >> 32)) : 3.402823466e+38f;
-        __syncthreads();  // everyone has read s_next / src[next] before they are rewritten
-        if (tid == 0) {
-            src[next] |= (uint64_t)kExpanded;
-            *c.s_cnt = 0;
-            *c.s_next = 0x7fffffff;
-        }
-        // visited table at > 1/2 load: rebuild it from the buffer (results unchanged, see header)
-        if (hcount > HS / 2) {
-            for (uint32_t i = tid; i < HS; i += kTeam) c.hash[i] = kEmpty;
+        const uint32_t *lst = g.list(node, level);
+        const bool hit = can_pref && node == pref_node;
+        // issue the list read before the barrier so its latency overlaps the bookkeeping
+        uint32_t nid0 = kEmpty;
+        if ((uint32_t)tid < llen) nid0 = hit ? c.pref[tid] : __ldg(lst + tid);
+        // visited table at > 5/8 load: rebuild it from the buffer (results unchanged, see header)
+        if (hcount > HS / 8 * 5) {
             __syncthreads();
-            for (int i = tid; i < size; i += kTeam) hash_insert(c.hash, c.hash_bits, (uint32_t)src[i] & kIdMask);
+            for (uint32_t i = tid; i < HS; i += TEAM) c.hash[i] = kEmpty;
+            __syncthreads();
+            for (int i = tid; i < size; i += TEAM) hash_insert(c.hash, c.hash_bits, (uint32_t)src[i] & kIdMask);
             hcount = size;
             w.resets += 1;
         }
-        __syncthreads();
-
-        // neighbour list of the expanded node -> unvisited ids, compacted into ids[]
-        const uint32_t *lst = g.list(node, level);
-        for (uint32_t b0 = 0; b0 < llen; b0 += kTeam) {
-            uint32_t nid = kEmpty;
-            if (b0 + tid < llen) nid = __ldg(lst + b0 + tid);
+        __syncthreads();  // (A) everyone has read s_next / src[next] / pref[]
+        if (tid == 0) {
+            src[next] |= (uint64_t)kExpanded;
+            *c.s_next = 0x7fffffff;
+        }
+        // neighbour list -> unvisited ids, compacted into ids[]
+        for (uint32_t b0 = 0; b0 < llen; b0 += TEAM) {
+            uint32_t nid = nid0;
+            if (b0) {
+                nid = kEmpty;
+                if (b0 + tid < llen) nid = __ldg(lst + b0 + tid);
+            }
             bool isnew = false;
             if (nid != kEmpty) isnew = hash_insert(c.hash, c.hash_bits, nid);
             const uint32_t m = __ballot_sync(0xffffffffu, isnew);
@@ -274,40 +365,42 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
             basepos = __shfl_sync(0xffffffffu, basepos, 0);
             if (isnew) c.ids[basepos + __popc(m & ((1u << lane) - 1u))] = nid;
         }
-        __syncthreads();
+        // the last warp predicts the next expansion: the first other unexpanded entry of the (pre-merge) buffer,
+        // and starts reading its list; the data lands in registers while everybody gathers vectors
+        uint32_t pf0 = kEmpty, pf1 = kEmpty, pnode = kEmpty;
+        if (can_pref && warp == TEAM / 32 - 1) {
+            const int pos = next + 1 + lane;
+            const bool un = pos < size && !((uint32_t)src[pos] & kExpanded);
+            const uint32_t b = __ballot_sync(0xffffffffu, un);
+            if (b) {
+                pnode = (uint32_t)src[next + __ffs(b)] & kIdMask;
+                const uint32_t *pl = g.list(pnode, level);
+                if ((uint32_t)lane < llen) pf0 = __ldg(pl + lane);
+                if ((uint32_t)lane + 32 < llen) pf1 = __ldg(pl + lane + 32);
+            }
+        }
+        __syncthreads();  // (B) ids[] complete
         const int nnew = *c.s_cnt;
         w.H0 += 1;
         w.D += nnew;
         hcount += nnew;
-        eval_list<LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, nnew, c.dist, grp, sub);
-        __syncthreads();
-        if (tid == 0) *c.s_cnt = 0;
-        __syncthreads();
-        // admit against the pre-expansion bound (hnswalg.h:395: size < ef || lowerBound > dist)
-        for (int b0 = 0; b0 < nnew; b0 += kTeam) {
-            bool ok = false;
-            uint64_t key = 0;
-            if (b0 + tid < nnew) {
-                const float dj = c.dist[b0 + tid];
-                ok = !full || dj < bound;
-                key = make_key(dj, c.ids[b0 + tid]);
-            }
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            int basepos = 0;
-            if (lane == 0 && m) basepos = atomicAdd(c.s_cnt, __popc(m));
-            basepos = __shfl_sync(0xffffffffu, basepos, 0);
-            if (ok) c.acc[basepos + __popc(m & ((1u << lane) - 1u))] = key;
+        eval_admit<TEAM, LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, nnew, full, bound, c.acc, c.s_acc, grp, sub);
+        if (can_pref && warp == TEAM / 32 - 1) {
+            if ((uint32_t)lane < llen) c.pref[lane] = pf0;
+            if ((uint32_t)lane + 32 < llen) c.pref[lane + 32] = pf1;
+            if (lane == 0) *c.s_pref = (int)pnode;
         }
-        __syncthreads();
-        const int m = *c.s_cnt;
+        __syncthreads();  // (C) acc[] complete, prefetched list stored
+        const int m = *c.s_acc;
+        pref_node = (uint32_t)*c.s_pref;
         int local_min = 0x7fffffff;
         if (m == 0) {
             // nothing admitted: buffer unchanged, find the next unexpanded entry after `next`
-            for (int i = next + 1 + tid; i < size; i += kTeam)
+            for (int i = next + 1 + tid; i < size; i += TEAM)
                 if (!((uint32_t)src[i] & kExpanded)) { local_min = i; break; }
         } else {
             // merge by rank: final position = own index + number of smaller keys in the other list
-            for (int i = tid; i < size; i += kTeam) {
+            for (int i = tid; i < size; i += TEAM) {
                 const uint64_t key = src[i];
                 const uint64_t km = key & kKeyMask;
                 int pos = i;
@@ -317,7 +410,7 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
                     if (!((uint32_t)key & kExpanded)) local_min = min(local_min, pos);
                 }
             }
-            for (int j = kTeam - 1 - tid; j < m; j += kTeam) {
+            for (int j = TEAM - 1 - tid; j < m; j += TEAM) {
                 const uint64_t key = c.acc[j];
                 int r = 0;
                 for (int i = 0; i < m; i++) r += (c.acc[i] < key) ? 1 : 0;
@@ -338,25 +431,19 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));
         if (lane == 0 && local_min != 0x7fffffff) atomicMin(c.s_next, local_min);
-        __syncthreads();
+        if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; }
+        __syncthreads();  // (D) merged buffer and s_next visible
     }
 }
 
-template <int LPV, int CPL, int METRIC>
-__global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) {
+template <int TEAM, int LPV, int CPL, int METRIC>
+__global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hnsw_search_kernel(const SearchArgs p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
     const SearchSmem L(p.ef, list_cap, p.d4, p.hash_bits);
-    __shared__ int s_ints[3];
+    __shared__ int s_ints[kTeamInts];
     TeamCtx c;
-    c.buf_a = (uint64_t *)(smem + L.off_buf0);
-    c.buf_b = (uint64_t *)(smem + L.off_buf1);
-    c.acc = (uint64_t *)(smem + L.off_acc);
-    c.ids = (uint32_t *)(smem + L.off_ids);
-    c.dist = (float *)(smem + L.off_dist);
-    c.hash = (uint32_t *)(smem + L.off_hash);
-    c.s_cnt = &s_ints[0]; c.s_next = &s_ints[1]; c.s_best = &s_ints[2];
-    c.hash_bits = p.hash_bits;
+    c.bind(smem, L, s_ints, p.hash_bits);
     float *qs = (float *)(smem + L.off_q);
     GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
 
@@ -367,9 +454,9 @@ __global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) 
     const uint32_t HS = 1u << p.hash_bits;
 
     // ---- stage the query (rows of Q are only 4-byte aligned when dim % 4 != 0) and clear the visited table ----
-    for (uint32_t i = tid; i < d4 * 4; i += kTeam) qs[i] = i < p.dim ? p.Q[(size_t)qi * p.dim + i] : 0.f;
-    for (uint32_t i = tid; i < HS; i += kTeam) c.hash[i] = kEmpty;
-    if (tid == 0) { *c.s_cnt = 0; *c.s_next = 0; }
+    for (uint32_t i = tid; i < d4 * 4; i += TEAM) qs[i] = i < p.dim ? p.Q[(size_t)qi * p.dim + i] : 0.f;
+    for (uint32_t i = tid; i < HS; i += TEAM) c.hash[i] = kEmpty;
+    if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; *c.s_next = 0; }
     __syncthreads();
     float4 q[CPL];
 #pragma unroll
@@ -383,20 +470,20 @@ __global__ void __launch_bounds__(kTeam) hnsw_search_kernel(const SearchArgs p) 
     uint32_t cur = p.entry;
     if (tid == 0) c.ids[0] = cur;
     __syncthreads();
-    eval_list<LPV, CPL, METRIC>(q, g.vec, d4, c.ids, 1, c.dist, grp, sub);
+    eval_list<TEAM, LPV, CPL, METRIC>(q, g.vec, d4, c.ids, 1, c.dist, grp, sub);
     __syncthreads();
     float curdist = c.dist[0];
     w.D += 1;
-    for (int level = p.maxlevel; level > 0; --level) greedy_level<LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
+    for (int level = p.maxlevel; level > 0; --level) greedy_level<TEAM, LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
     __syncthreads();
 
     // ---- searchBaseLayerST on level 0 ----
     int cb, size;
-    beam_level<LPV, CPL, METRIC>(c, q, g, 0, p.ef, cur, curdist, cb, size, w);
+    beam_level<TEAM, LPV, CPL, METRIC>(c, q, g, 0, p.ef, cur, curdist, cb, size, w);
 
     // ---- epilogue: first k entries are the result, closest first (hnswalg.h:1315-1322) ----
     const uint64_t *res = cb ? c.buf_b : c.buf_a;
-    for (uint32_t j = tid; j < p.k; j += kTeam) {
+    for (uint32_t j = tid; j < p.k; j += TEAM) {
         uint64_t lab = 0xFFFFFFFFFFFFFFFFull;
         float dj = __int_as_float(0x7f800000);
         if (j < (uint32_t)size) {

@@ -132,3 +132,21 @@ def test_visited_table_rebuild_keeps_results(lib, orc, graphs, monkeypatch):
     assert r["resets"].sum() > 0
     _check(r, cpu, "rebuild")
     assert (r["D"] + 1 >= cpu["D"]).all()
+
+
+def test_merge_topk_kernel_matches_reference_semantics(lib):
+    """k-way merge of per-shard rows vs the numpy statement of the same contract."""
+    import torch
+    from research_new_hnsw_b200.sharded import cuda_merge, merge_topk_numpy
+    rng = np.random.default_rng(5)
+    for shards, nq, k in [(2, 100, 10), (8, 257, 10), (4, 33, 100), (3, 5, 1)]:
+        D = np.sort(rng.random((shards, nq, k), dtype=np.float32), axis=2)
+        D[:, :, k // 2:] = np.round(D[:, :, k // 2:], 1)                      # force ties across shards
+        D = np.sort(D, axis=2)
+        L = rng.permutation(shards * nq * k).astype(np.uint64).reshape(shards, nq, k)
+        D[0, 0, k - 1] = np.inf
+        L[0, 0, k - 1] = np.uint64(0xFFFFFFFFFFFFFFFF)                         # a padded slot
+        el, ed = merge_topk_numpy(L, D, k)
+        gl, gd = cuda_merge()(torch.from_numpy(L.view(np.int64)).cuda(), torch.from_numpy(D).cuda(), k)
+        torch.cuda.synchronize()
+        assert np.array_equal(gl.cpu().numpy().view(np.uint64), el) and np.array_equal(gd.cpu().numpy(), ed)
