@@ -78,7 +78,7 @@ typedef struct {
 typedef struct {
     uint64_t queries;
     uint64_t dist_evals;     /* D: vectors read and compared, all layers */
-    uint64_t hops_base;      /* H0: level-0 expansions */
+    uint64_t hops_base;      /* H0: level-0 expansions (brute force: 1 if the tensor-core path produced the result) */
     uint64_t hops_upper;     /* Hup: upper-layer list scans */
     uint64_t visited_resets; /* times a per-query visited table was rebuilt (re-evaluations possible, results unchanged) */
     uint64_t kernel_launches;

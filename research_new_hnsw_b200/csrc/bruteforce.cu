@@ -234,6 +234,7 @@ __global__ void bf_pad_rows_kernel(const float *__restrict__ X, uint32_t dim, ui
 }
 
 BruteIndex::~BruteIndex() {
+    tz.release();
     cudaFree(dX); cudaFree(dLabels); cudaFree(dQ); cudaFree(dOutL); cudaFree(dOutD); cudaFree(dPartL);
     cudaFree(dPartD); cudaFree(dCounts);
     if (ev0) cudaEventDestroy(ev0);
@@ -312,6 +313,11 @@ int BruteIndex::upload_rows(size_t first, size_t count) {
         }
     }
     cudaFree(draw);
+    if (tz.xb) {  // keep the bf16 copy of the tensor path in step
+        int rc = tensor_sync_rows(first, count);
+        if (rc) return rc;
+        B200_CUDA_OK(cudaDeviceSynchronize());
+    }
     return 0;
 }
 
@@ -370,11 +376,27 @@ int BruteIndex::ensure_part(size_t elems) {
     return 0;
 }
 
+// Path choice: the tensor-core candidate generator pays off once the scan is a real GEMM (rows x queries large);
+// small problems and anything it cannot bound go to the exact scan.  B200HNSW_BF_PATH=scan|tensor forces one.
 int BruteIndex::search_device(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc,
                               cudaStream_t st) {
     if (nq == 0) return 0;
     if (!dQ_ || !dl || !dd || k == 0) { set_error("search: null pointer or k == 0"); return B200HNSW_E_ARG; }
     B200_CUDA_OK(cudaSetDevice(device));
+    const char *force = getenv("B200HNSW_BF_PATH");
+    const bool want_scan = force && !strcmp(force, "scan");
+    const bool want_tensor = force && !strcmp(force, "tensor");
+    const size_t n = host.cur;
+    if (!want_scan && k <= n && (want_tensor || (double)n * (double)nq >= 6.7e7)) {
+        const int rc = search_tensor(dQ_, nq, k, dl, dd, dc, st);
+        if (rc <= 0) { last_path = 1; return rc; }  // done, or a real error; rc == 1 -> fall through to the scan
+    }
+    last_path = 0;
+    return search_scan(dQ_, nq, k, dl, dd, dc, st);
+}
+
+int BruteIndex::search_scan(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc,
+                            cudaStream_t st) {
     const size_t n = host.cur;
     const BfSmem L((uint32_t)k);
     if (L.total > 227 * 1024) { set_error("k too large for the brute-force kernel"); return B200HNSW_E_UNSUPPORTED; }
@@ -455,6 +477,8 @@ int BruteIndex::search_host(const float *Q, size_t nq, size_t k, uint64_t *label
     stats.last_kernel_ms = ms;
     stats.queries = nq;
     stats.dist_evals = (uint64_t)nq * host.cur;
+    stats.hops_base = (uint64_t)last_path;  // 1: tcgen05 candidate GEMM + exact re-rank, 0: exact scan
+    stats.hops_upper = tz.last_candidates;  // candidates re-ranked (only with B200HNSW_BF_STATS)
     return 0;
 }
 

@@ -15,6 +15,17 @@
 
 namespace b200 {
 
+// Device state of the tensor-core candidate generator (bf_tensor.cu).
+struct BruteTensor {
+    void *xb = nullptr;        // bf16 [rows_pad][kp]
+    float *xn2 = nullptr;      // [rows_pad] squared norms
+    void *qb = nullptr;        // bf16 [q_cap][kp]
+    float *qn2 = nullptr, *thr = nullptr;
+    uint32_t *panelmin = nullptr, *cand = nullptr, *cand_cnt = nullptr, *overflow = nullptr;
+    size_t kp = 0, rows_pad = 0, q_cap = 0, cap = 0, pm_elems = 0, last_candidates = 0;
+    void release();
+};
+
 struct BruteIndex {
     b200hnsw_params prm{};
     HostBrute host;
@@ -24,6 +35,8 @@ struct BruteIndex {
     uint64_t *dLabels = nullptr;
     std::mutex mu;
     b200hnsw_stats stats{};
+    BruteTensor tz;
+    int last_path = 0;  // 0 = exact scan, 1 = tensor-core candidates + exact re-rank
     // scratch
     float *dQ = nullptr;
     uint64_t *dOutL = nullptr, *dPartL = nullptr;
@@ -43,6 +56,10 @@ struct BruteIndex {
     int ensure_part(size_t elems);
     int search_device(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
     int search_host(const float *Q, size_t nq, size_t k, uint64_t *labels, float *dists, uint32_t *counts);
+    // bf_tensor.cu
+    int tensor_sync_rows(size_t first, size_t count);
+    int search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
+    int search_scan(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
 };
 
 }  // namespace b200

@@ -70,3 +70,30 @@ def test_k_larger_than_count(lib):
     r = g.searchKnnBatch(X[:1], 6)
     assert r["counts"][0] == 3 and r["labels"][0, :3].tolist() == [0, 1, 2]
     assert np.isinf(r["dists"][0, 3:]).all()
+
+
+@pytest.mark.parametrize("metric,n,d,k,nq", [(bind.L2, 40000, 128, 10, 300), (bind.IP, 30000, 768, 100, 130),
+                                             (bind.L2, 20000, 100, 5, 257), (bind.IP, 33000, 30, 20, 64)])
+def test_tensor_core_path_is_exact(lib, orc, monkeypatch, metric, n, d, k, nq):
+    """tcgen05 GEMM candidate generation + exact re-rank (csrc/bf_tensor.cu): same bar as the scan -- ids bit-exact,
+    distances bit-identical -- because the re-rank uses the reference's summation order."""
+    monkeypatch.setenv("B200HNSW_BF_PATH", "tensor")
+    X = bind.lowrank_data(n, d, seed=51, latent=24, noise=0.2, normalize=(metric == bind.IP))
+    X[n // 2] = X[n // 3]
+    Q = bind.lowrank_data(nq, d, seed=52, latent=24, noise=0.2, normalize=(metric == bind.IP))
+    labels = (np.arange(n, dtype=np.uint64) * 3 + 1)
+    space = lib.L2Space(d) if metric == bind.L2 else lib.InnerProductSpace(d)
+    g = lib.BruteforceSearch(space, n)
+    g.addPoints(X, labels)
+    rg = g.searchKnnBatch(Q, k)
+    assert g.stats()["hops_base"] == 1, "tensor path did not run"
+    c = orc.bf_new(metric, d, n)
+    c.add(X, labels)
+    rc = c.search(Q[:40], k)
+    assert np.array_equal(rg["labels"][:40], rc["labels"])
+    assert np.array_equal(rg["dists"][:40], rc["dists"])
+    monkeypatch.setenv("B200HNSW_BF_PATH", "scan")
+    rs = g.searchKnnBatch(Q, k)                                  # all queries against the exact scan kernel
+    assert g.stats()["hops_base"] == 0
+    assert np.array_equal(rg["labels"], rs["labels"]) and np.array_equal(rg["dists"], rs["dists"])
+    assert np.array_equal(rg["counts"], rs["counts"])
