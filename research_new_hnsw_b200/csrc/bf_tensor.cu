@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "bruteforce.cuh"
+#include "search_kernel.cuh"  // eval_list: the coalesced fp32 gather
 
 namespace b200 {
 
@@ -45,8 +46,8 @@ constexpr float kErrDelta = 4e-6f;
 
 struct GemmArgs {
     const float *xn2;       // [rows] squared norms (fp32)
-    const float *qn2;       // [nq_pad]
-    const float *thr;       // [nq_pad] U(q)  (pass 2)
+    const float *tabB;      // [nq_pad] per-query error slope  (bf_tables_kernel)
+    const float *tabT;      // [nq_pad] per-query additive term / threshold
     uint32_t *panelmin;     // [sampled panels][nq_pad] ordered floats (pass 1)
     uint32_t *cand;         // [nq][cap] row ids (pass 2)
     uint32_t *cand_cnt;     // [nq]
@@ -122,10 +123,6 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
     uint64_t *tfull = empty + kGStages;           // [2]
     uint64_t *tempty = tfull + 2;                 // [2]
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
-    float *s_qn2 = (float *)(tail + 256);         // [kGN]
-    float *s_cq = s_qn2 + kGN;                    // [kGN]  c * |q|
-    float *s_thr = s_cq + kGN;                    // [kGN]
-    uint32_t *s_colmin = (uint32_t *)(s_thr + kGN);  // [kGN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sampled = (a.panels + a.stride - 1) / a.stride;
@@ -186,61 +183,112 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         }
     } else {
         // ===== epilogue warps: TMEM lane quarter = warp % 4 =====
+        // Per element (row r = TMEM lane, query column j):  w = fma(+-B_j, |x_r|, alpha * S)  with alpha = -1 (IP) / -2 (L2),
+        //   pass 1 (MODE 0): min over the 32 rows of a warp of  w + Ar  (+ T_j once per column), Ar = (1+delta)|x|^2 (L2) / 0
+        //   pass 2 (MODE 1): hit iff  w <= T_j - Ar,                                   Ar = (1-delta)|x|^2 (L2) / 0
+        // B_j, T_j come from bf_tables_kernel.  The 32 columns of a chunk are evaluated branch-free into a bit mask;
+        // only chunks that contain a hit (rare) walk their set bits.  Tables of the next item are prefetched into
+        // registers while this one is processed and live double-buffered in shared memory.
         const int quarter = warp & 3;
         const int et = threadIdx.x - 64;  // 0..127
-        uint32_t buf = 0, bphase = 0;
-        for (uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
-            const uint32_t pi = it / a.qtiles, p = pi * a.stride, t = it % a.qtiles;
-            // per-tile query tables
-            for (int j = et; j < kGN; j += 128) {
-                const uint32_t q = t * kGN + j;
-                const float qn2 = a.qn2[q];
-                s_qn2[j] = qn2;
-                s_cq[j] = kErrC * sqrtf(qn2);
-                if (MODE == 1) s_thr[j] = a.thr[q];
-                if (MODE == 0) s_colmin[j] = 0xFFFFFFFFu;
+        float *s_B = (float *)(tail + 256);          // [2][kGN]
+        float *s_T = s_B + 2 * kGN;                  // [2][kGN]
+        uint32_t *s_min = (uint32_t *)(s_T + 2 * kGN);  // [2][kGN] (pass 1)
+        constexpr float alpha = METRIC == 1 ? -1.f : -2.f;
+        uint32_t buf = 0, bphase = 0, tb = 0;
+        float pB[2], pT[2];
+        uint32_t it = blockIdx.x;
+        if (it < items) {
+            const uint32_t t = it % a.qtiles;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const uint32_t q = t * kGN + et + e * 128;
+                s_B[et + e * 128] = a.tabB[q];
+                s_T[et + e * 128] = a.tabT[q];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        s_min[et] = s_min[et + 128] = s_min[kGN + et] = s_min[kGN + et + 128] = 0xFFFFFFFFu;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t prev_pi = 0, prev_t = 0;
+        bool have_prev = false;
+        for (; it < items; it += gridDim.x) {
+            const uint32_t pi = it / a.qtiles, p = pi * a.stride, t = it % a.qtiles;
+            const uint32_t nit = it + gridDim.x;
+            if (nit < items) {  // prefetch the next item's tables
+                const uint32_t nt = nit % a.qtiles;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const uint32_t q = nt * kGN + et + e * 128;
+                    pB[e] = a.tabB[q];
+                    pT[e] = a.tabT[q];
+                }
+            }
+            if (MODE == 0 && have_prev) {  // flush the previous item's column minima (other table buffer)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = et + e * 128;
+                    a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
+                    s_min[(tb ^ 1) * kGN + j] = 0xFFFFFFFFu;
+                }
+            }
+            const float *B = s_B + tb * kGN, *T = s_T + tb * kGN;
             const uint32_t r = p * kGM + quarter * 32 + lane;
             const bool rvalid = r < a.n;
             const float xn2 = rvalid ? a.xn2[r] : 0.f;
             const float xnorm = sqrtf(xn2);
+            const float Ar = METRIC == 1 ? 0.f : (MODE == 0 ? (1.f + kErrDelta) : (1.f - kErrDelta)) * xn2;
+            const float bx = MODE == 0 ? xnorm : -xnorm;
             mbar_wait(tfull + buf, bphase);
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < kGN / 32; c++) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kGN + c * 32, v);
-                tc_wait_ld();
+                float Bc[32], Tc[32];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int col = c * 32 + j;
-                    const float s = __uint_as_float(v[j]);
-                    float key, err;
-                    if (METRIC == 1) {
-                        key = -s;
-                        err = s_cq[col] * xnorm;
-                    } else {
-                        const float sum = xn2 + s_qn2[col];
-                        key = fmaf(-2.f, s, sum);
-                        err = fmaf(2.f * s_cq[col], xnorm, kErrDelta * sum);
+                for (int j4 = 0; j4 < 8; j4++) {
+                    const float4 b4 = *(const float4 *)(B + c * 32 + j4 * 4);
+                    Bc[j4 * 4] = b4.x; Bc[j4 * 4 + 1] = b4.y; Bc[j4 * 4 + 2] = b4.z; Bc[j4 * 4 + 3] = b4.w;
+                    if (MODE == 1) {
+                        const float4 t4 = *(const float4 *)(T + c * 32 + j4 * 4);
+                        Tc[j4 * 4] = t4.x; Tc[j4 * 4 + 1] = t4.y; Tc[j4 * 4 + 2] = t4.z; Tc[j4 * 4 + 3] = t4.w;
                     }
-                    if (MODE == 0) {
-                        const uint32_t o = rvalid ? f2ord(key + err) : 0xFFFFFFFFu;
+                }
+                tc_wait_ld();
+                if (MODE == 0) {
+                    uint32_t mine = 0xFFFFFFFFu;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float w = fmaf(Bc[j], bx, alpha * __uint_as_float(v[j])) + Ar;
+                        const uint32_t o = rvalid ? f2ord(w) : 0xFFFFFFFFu;
                         const uint32_t m = __reduce_min_sync(0xffffffffu, o);
-                        if (lane == 0) atomicMin(&s_colmin[col], m);
-                    } else {
-                        const uint32_t q = t * kGN + col;
-                        const bool hit = rvalid && q < a.nq && (key - err) <= s_thr[col];
+                        mine = lane == j ? m : mine;
+                    }
+                    // lane j now holds the warp's minimum of column c*32+j; T_j is added once per column
+                    if (mine != 0xFFFFFFFFu)
+                        atomicMin(&s_min[tb * kGN + c * 32 + lane], f2ord(ord2f(mine) + T[c * 32 + lane]));
+                } else {
+                    uint32_t hits = 0;
+                    const float rhs_r = -Ar;
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float w = fmaf(Bc[j], bx, alpha * __uint_as_float(v[j]));
+                        hits |= (w <= Tc[j] + rhs_r) ? (1u << j) : 0u;
+                    }
+                    if (!rvalid) hits = 0;
+                    uint32_t any = __reduce_or_sync(0xffffffffu, hits);
+                    while (any) {  // rare: columns with at least one admitted row
+                        const int j = __ffs(any) - 1;
+                        any &= any - 1;
+                        const uint32_t q = t * kGN + c * 32 + j;
+                        const bool hit = (hits >> j) & 1u;
                         const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                        if (m) {
-                            uint32_t base = 0;
-                            if (lane == 0) base = atomicAdd(a.cand_cnt + q, (uint32_t)__popc(m));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            if (hit) {
-                                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                                if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = r;
-                            }
+                        uint32_t base = 0;
+                        if (lane == 0) base = atomicAdd(a.cand_cnt + q, (uint32_t)__popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (hit) {
+                            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                            if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = r;
                         }
                     }
                 }
@@ -248,10 +296,23 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             tc_fence_before();
             if (lane == 0) mbar_arrive(tempty + buf);  // this warp is done with the accumulator
             if (++buf == 2) { buf = 0; bphase ^= 1; }
+            if (nit < items) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    s_B[(tb ^ 1) * kGN + et + e * 128] = pB[e];
+                    s_T[(tb ^ 1) * kGN + et + e * 128] = pT[e];
+                }
+            }
+            prev_pi = pi; prev_t = t; have_prev = true;
+            tb ^= 1;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (MODE == 0)
-                for (int j = et; j < kGN; j += 128) a.panelmin[(size_t)pi * a.nq_pad + t * kGN + j] = s_colmin[j];
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        if (MODE == 0 && have_prev) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int j = et + e * 128;
+                a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
+            }
         }
     }
     tc_fence_before();
@@ -281,87 +342,206 @@ __global__ void bf_to_bf16_kernel(const float *__restrict__ src, size_t src_stri
     if (lane == 0 && n2) n2[r] = acc;
 }
 
-// U(q) = k-th smallest of the sampled panel minima (bitwise binary search over the ordered-float domain).
-__global__ void bf_kth_kernel(const uint32_t *__restrict__ panelmin, uint32_t sampled, uint32_t nq_pad, uint32_t nq,
-                              uint32_t k, float *__restrict__ thr) {
+// Per-query epilogue tables.  pass 1: B = c|q| (IP) / 2c|q| (L2), T = 0 / (1+delta)|q|^2.
+//                            pass 2: B as above,             T = U(q) / U(q) - (1-delta)|q|^2.
+__global__ void bf_tables_kernel(const float *__restrict__ qn2, const float *__restrict__ thr, uint32_t nq_pad, int metric,
+                                 int mode, float *__restrict__ tabB, float *__restrict__ tabT) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq_pad) return;
-    if (q >= nq || sampled < k) { thr[q] = q >= nq ? -3.402823466e+38f : 3.402823466e+38f; return; }
+    const float n2 = qn2[q], cq = kErrC * sqrtf(n2);
+    if (metric == 1) {
+        tabB[q] = cq;
+        tabT[q] = mode == 0 ? 0.f : thr[q];
+    } else {
+        tabB[q] = 2.f * cq;
+        tabT[q] = mode == 0 ? (1.f + kErrDelta) * n2 : thr[q] - (1.f - kErrDelta) * n2;
+    }
+}
+
+// U(q) = k-th smallest of the sampled panel minima (bitwise binary search over the ordered-float domain).
+// Block = 32 queries x 8 slices of the panel range; loads are coalesced over queries.
+__global__ void __launch_bounds__(256) bf_kth_kernel(const uint32_t *__restrict__ panelmin, uint32_t sampled,
+                                                     uint32_t nq_pad, uint32_t nq, uint32_t k, float *__restrict__ thr) {
+    __shared__ uint32_t part[8][32];
+    const uint32_t x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x * 32 + x;  // nq_pad is a multiple of 256, so q < nq_pad
     uint32_t prefix = 0;
     for (int bit = 31; bit >= 0; bit--) {
         const uint32_t cand = prefix | ((1u << bit) - 1u);  // largest value with this prefix and bit = 0
         uint32_t cnt = 0;
-        for (uint32_t g = 0; g < sampled; g++) cnt += panelmin[(size_t)g * nq_pad + q] <= cand ? 1u : 0u;
-        if (cnt < k) prefix |= 1u << bit;
+        for (uint32_t g = y; g < sampled; g += 8) cnt += panelmin[(size_t)g * nq_pad + q] <= cand ? 1u : 0u;
+        part[y][x] = cnt;
+        __syncthreads();
+        uint32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) tot += part[i][x];
+        __syncthreads();
+        if (tot < k) prefix |= 1u << bit;
     }
-    thr[q] = ord2f(prefix);
+    if (y == 0) thr[q] = q >= nq ? -3.402823466e+38f : (sampled < k ? 3.402823466e+38f : ord2f(prefix));
 }
 
-// Exact distance in the reference's SSE order (same arithmetic as bf_scan_kernel): q in shared memory, x a padded row.
-template <int METRIC>
-__device__ __forceinline__ float exact_dist(const float *q, const float4 *__restrict__ x, uint32_t d4, uint32_t lane_chunks) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t = 0.f;
-    for (uint32_t c = 0; c < d4; c++) {
-        const float4 xv = __ldg(x + c);
-        const float4 qv = *(const float4 *)(q + 4 * c);
-        float m0, m1, m2, m3;
-        if (METRIC == 0) {
-            const float a0 = __fsub_rn(qv.x, xv.x), a1 = __fsub_rn(qv.y, xv.y), a2 = __fsub_rn(qv.z, xv.z), a3 = __fsub_rn(qv.w, xv.w);
-            m0 = __fmul_rn(a0, a0); m1 = __fmul_rn(a1, a1); m2 = __fmul_rn(a2, a2); m3 = __fmul_rn(a3, a3);
-        } else {
-            m0 = __fmul_rn(qv.x, xv.x); m1 = __fmul_rn(qv.y, xv.y); m2 = __fmul_rn(qv.z, xv.z); m3 = __fmul_rn(qv.w, xv.w);
-        }
-        if (c < lane_chunks) {
-            s0 = __fadd_rn(s0, m0); s1 = __fadd_rn(s1, m1); s2 = __fadd_rn(s2, m2); s3 = __fadd_rn(s3, m3);
-        } else {
-            t = __fadd_rn(t, m0); t = __fadd_rn(t, m1); t = __fadd_rn(t, m2); t = __fadd_rn(t, m3);
-        }
-    }
-    float r = __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
-    r = __fadd_rn(r, t);
-    if (METRIC == 1) r = __fsub_rn(1.0f, r);
-    return r;
-}
+// Re-rank, one CTA per query, in three steps:
+//  A. fast fp32 distances of all candidates: one warp per candidate, coalesced 128-bit loads, FFMA2, shuffle reduce
+//     (the gather of the graph-search kernel, eval_list<.., LPV=32, ..>);
+//  B. bound: U2 = k-th smallest of (fast + E2) with E2 >= |fast - reference-order value|
+//     (E2 = e2 * |q||x| for inner product, e2 * fast for L2 whose terms are all non-negative); survivors are the
+//     candidates with fast - E2 <= U2 -- the true top-k plus near-ties, typically k + a handful;
+//  C. exact distances of the survivors in the reference's SSE order (same arithmetic as bf_scan_kernel: four lane
+//     accumulators over the first lane_chunks 128-bit chunks, sequential tail, separate multiply and add), rows staged
+//     through shared memory 32 floats at a time so global reads stay coalesced while every thread sums ITS
+//     candidate strictly in index order; then the k smallest (dist, label) by rank, closest first.
+constexpr int kRrThreads = 256;
+constexpr int kRrRows = 128;   // survivor rows staged per round of step C
+constexpr int kRrStride = 33;  // floats per staged row (+1: conflict-free column walks)
 
-// One CTA per query: exact distances of its candidates, k smallest (dist, label) by rank, closest first.
-template <int METRIC>
-__global__ void __launch_bounds__(256) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
-                                                        const float *__restrict__ Q, uint32_t dim, uint32_t d4,
-                                                        uint32_t lane_chunks, const uint32_t *__restrict__ cand,
-                                                        const uint32_t *__restrict__ cand_cnt, uint32_t cap, uint32_t k,
-                                                        uint32_t n, uint64_t *__restrict__ out_l, float *__restrict__ out_d,
-                                                        uint32_t *__restrict__ out_c, uint32_t *__restrict__ overflow) {
+template <int METRIC, int CPL>
+__global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
+                                                              const float *__restrict__ xn2, const float *__restrict__ qn2,
+                                                              const float *__restrict__ Q, uint32_t dim, uint32_t d4,
+                                                              uint32_t lane_chunks, const uint32_t *__restrict__ cand,
+                                                              const uint32_t *__restrict__ cand_cnt, uint32_t cap, uint32_t k,
+                                                              uint32_t n, float e2, uint64_t *__restrict__ out_l,
+                                                              float *__restrict__ out_d, uint32_t *__restrict__ out_c,
+                                                              uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char sm[];
-    float *qs = (float *)sm;                        // [d4*4]
-    float *cd = qs + d4 * 4;                        // [cap]
-    uint64_t *cl = (uint64_t *)(cd + cap + (cap & 1));  // [cap]
+    float *qs = (float *)sm;                              // [d4*4]
+    float *fd = qs + d4 * 4;                              // [cap] fast distances, later exact distances of survivors
+    uint32_t *ids = (uint32_t *)(fd + cap);               // [cap] candidate rows, later survivor rows
+    uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [cap] survivor labels
+    float *tile = (float *)(cl + cap);                    // [max(kRrRows*kRrStride, cap)]
+    __shared__ uint32_t s_part[kRrThreads / 32];
+    __shared__ uint32_t s_cnt;
     const uint32_t q = blockIdx.x;
-    const uint32_t cnt_raw = cand_cnt[q];
-    if (cnt_raw > cap) {  // candidate buffer overflowed: this batch is redone by the exact scan
+    const uint32_t cnt = cand_cnt[q];
+    if (cnt > cap) {  // candidate buffer overflowed: this batch is redone by the exact scan
         if (threadIdx.x == 0) atomicAdd(overflow, 1u);
         return;
     }
-    const uint32_t cnt = cnt_raw;
-    for (uint32_t i = threadIdx.x; i < d4 * 4; i += blockDim.x) qs[i] = i < dim ? Q[(size_t)q * dim + i] : 0.f;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < d4 * 4; i += kRrThreads) qs[i] = i < dim ? Q[(size_t)q * dim + i] : 0.f;
+    for (uint32_t i = tid; i < cnt; i += kRrThreads) ids[i] = cand[(size_t)q * cap + i];
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const uint32_t r = cand[(size_t)q * cap + i];
-        cd[i] = exact_dist<METRIC>(qs, X + (size_t)r * d4, d4, lane_chunks);
-        cl[i] = labels[r];
+    // ---- A: fast distances ----
+    {
+        float4 qr[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; c++) {
+            const uint32_t idx = lane + c * 32;
+            qr[c] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        eval_list<kRrThreads, 32, CPL, METRIC>(qr, X, d4, ids, (int)cnt, fd, warp, lane);
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) {  // padding for rows the ranks below do not fill
-        if (j >= cnt) {
+    // ---- B: U2 = k-th smallest of fast + E2 (bitwise binary search over ordered floats) ----
+    const float qn = sqrtf(qn2[q]);
+    float2 *he = (float2 *)cl;  // (fast + E2, fast - E2); cl[] proper is only written in step C
+    for (uint32_t i = tid; i < cnt; i += kRrThreads) {
+        const float f = fd[i];
+        const float e = METRIC == 1 ? e2 * qn * sqrtf(xn2[ids[i]]) : e2 * fabsf(f);
+        he[i] = make_float2(f + e, f - e);
+    }
+    __syncthreads();
+    uint32_t prefix = 0;
+    if (cnt > k) {
+        for (int bit = 31; bit >= 0; bit--) {
+            const uint32_t cval = prefix | ((1u << bit) - 1u);
+            uint32_t c = 0;
+            for (uint32_t i = tid; i < cnt; i += kRrThreads) c += f2ord(he[i].x) <= cval ? 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) s_part[warp] = c;
+            __syncthreads();
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < kRrThreads / 32; w++) tot += s_part[w];
+            __syncthreads();
+            if (tot < k) prefix |= 1u << bit;
+        }
+    } else {
+        prefix = 0xFFFFFFFFu;
+    }
+    const float u2 = ord2f(prefix);
+    // survivors, compacted in place (tile[] is reused as a staging list first)
+    uint32_t *surv = (uint32_t *)tile;
+    for (uint32_t b0 = 0; b0 < cnt; b0 += kRrThreads) {
+        const uint32_t i = b0 + tid;
+        const bool keep = i < cnt && (cnt <= k || he[i].y <= u2);
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) surv[base + __popc(m & ((1u << lane) - 1u))] = ids[i];
+    }
+    __syncthreads();
+    const uint32_t ns = s_cnt;  // <= cnt <= cap words fit in tile[] (sized max(kRrRows*kRrStride, cap))
+    for (uint32_t i = tid; i < ns; i += kRrThreads) ids[i] = surv[i];
+    __syncthreads();
+    // ---- C: exact distances of the survivors in reference order ----
+    for (uint32_t base = 0; base < ns; base += kRrRows) {
+        const uint32_t nb = min((uint32_t)kRrRows, ns - base);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t = 0.f;
+        for (uint32_t c0 = 0; c0 < d4; c0 += 8) {  // 8 float4 = 32 floats = 128 bytes per row and stage
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < kRrRows * 8 / kRrThreads; i++) {
+                const uint32_t f = tid + kRrThreads * i;  // float4 slot: candidate f/8, part f%8
+                const uint32_t cj = f >> 3, part = f & 7;
+                if (cj < nb) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c0 + part < d4) v = __ldg(X + (size_t)ids[base + cj] * d4 + c0 + part);
+                    float *dst = tile + cj * kRrStride + part * 4;
+                    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                }
+            }
+            __syncthreads();
+            if ((uint32_t)tid < nb) {
+                const float *row = tile + tid * kRrStride;
+#pragma unroll
+                for (int part = 0; part < 8; part++) {
+                    const uint32_t c = c0 + part;
+                    if (c < d4) {
+                        const float4 qv = *(const float4 *)(qs + 4 * c);
+                        const float x0 = row[part * 4], x1 = row[part * 4 + 1], x2 = row[part * 4 + 2], x3 = row[part * 4 + 3];
+                        float m0, m1, m2, m3;
+                        if (METRIC == 0) {
+                            const float a0 = __fsub_rn(qv.x, x0), a1 = __fsub_rn(qv.y, x1), a2 = __fsub_rn(qv.z, x2), a3 = __fsub_rn(qv.w, x3);
+                            m0 = __fmul_rn(a0, a0); m1 = __fmul_rn(a1, a1); m2 = __fmul_rn(a2, a2); m3 = __fmul_rn(a3, a3);
+                        } else {
+                            m0 = __fmul_rn(qv.x, x0); m1 = __fmul_rn(qv.y, x1); m2 = __fmul_rn(qv.z, x2); m3 = __fmul_rn(qv.w, x3);
+                        }
+                        if (c < lane_chunks) {
+                            s0 = __fadd_rn(s0, m0); s1 = __fadd_rn(s1, m1); s2 = __fadd_rn(s2, m2); s3 = __fadd_rn(s3, m3);
+                        } else {
+                            t = __fadd_rn(t, m0); t = __fadd_rn(t, m1); t = __fadd_rn(t, m2); t = __fadd_rn(t, m3);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if ((uint32_t)tid < nb) {
+            float r = __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+            r = __fadd_rn(r, t);
+            if (METRIC == 1) r = __fsub_rn(1.0f, r);
+            fd[base + tid] = r;
+            cl[base + tid] = labels[ids[base + tid]];
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = tid; j < k; j += kRrThreads) {  // padding for rows the ranks below do not fill
+        if (j >= ns) {
             out_l[(size_t)q * k + j] = 0xFFFFFFFFFFFFFFFFull;
             out_d[(size_t)q * k + j] = __int_as_float(0x7f800000);
         }
     }
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-        const float di = cd[i];
+    for (uint32_t i = tid; i < ns; i += kRrThreads) {
+        const float di = fd[i];
         const uint64_t li = cl[i];
         uint32_t rank = 0;
-        for (uint32_t j = 0; j < cnt; j++) {
-            const float dj = cd[j];
+        for (uint32_t j = 0; j < ns; j++) {
+            const float dj = fd[j];
             rank += (dj < di || (dj == di && cl[j] < li)) ? 1u : 0u;
         }
         if (rank < k) {
@@ -369,7 +549,30 @@ __global__ void __launch_bounds__(256) bf_rerank_kernel(const float4 *__restrict
             out_d[(size_t)q * k + rank] = di;
         }
     }
-    if (threadIdx.x == 0 && out_c) out_c[q] = min(min(k, n), cnt);
+    if (tid == 0 && out_c) out_c[q] = min(min(k, n), ns);
+}
+
+template <int METRIC>
+static void launch_rerank(uint32_t d4, unsigned grid, size_t smem, cudaStream_t st, const float4 *X, const uint64_t *labels,
+                          const float *xn2, const float *qn2, const float *Q, uint32_t dim, uint32_t lane_chunks,
+                          const uint32_t *cand, const uint32_t *cand_cnt, uint32_t cap, uint32_t k, uint32_t n, float e2,
+                          uint64_t *out_l, float *out_d, uint32_t *out_c, uint32_t *overflow) {
+#define B200_RR(CPL)                                                                                                     \
+    do {                                                                                                                 \
+        static bool cfg = false;                                                                                         \
+        if (!cfg) {                                                                                                      \
+            cudaFuncSetAttribute(bf_rerank_kernel<METRIC, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            cfg = true;                                                                                                  \
+        }                                                                                                                \
+        bf_rerank_kernel<METRIC, CPL><<<grid, kRrThreads, smem, st>>>(X, labels, xn2, qn2, Q, dim, d4, lane_chunks, cand, \
+                                                                      cand_cnt, cap, k, n, e2, out_l, out_d, out_c, overflow); \
+    } while (0)
+    if (d4 <= 32) B200_RR(1);
+    else if (d4 <= 64) B200_RR(2);
+    else if (d4 <= 128) B200_RR(4);
+    else if (d4 <= 192) B200_RR(6);
+    else B200_RR(8);
+#undef B200_RR
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -405,7 +608,8 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t kp
 }
 
 void BruteTensor::release() {
-    cudaFree(xb); cudaFree(xn2); cudaFree(qb); cudaFree(qn2); cudaFree(thr); cudaFree(panelmin); cudaFree(cand);
+    cudaFree(xb); cudaFree(xn2); cudaFree(qb); cudaFree(qn2); cudaFree(thr); cudaFree(tabB); cudaFree(tabT);
+    cudaFree(panelmin); cudaFree(cand);
     cudaFree(cand_cnt); cudaFree(overflow);
     *this = BruteTensor();
 }
@@ -440,6 +644,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     if (const char *e = getenv("B200HNSW_BF_SAMPLE")) stride = std::max(1, atoi(e));
     while (stride > 1 && (panels + stride - 1) / stride < 2 * k) stride /= 2;
     if ((panels + stride - 1) / stride < k) return 1;
+    if (d4 > 256) return 1;  // dim > 1024: exact scan
     int rc = 0;
     if (!tz.xb) {  // first use: bf16 copy + norms of everything stored so far (kept in sync by upload_rows afterwards)
         rc = tensor_sync_rows(0, n);
@@ -449,14 +654,20 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const size_t kp = tz.kp;
     const size_t nq_pad = (nq + kGN - 1) / kGN * kGN;
     const size_t sampled = (panels + stride - 1) / stride;
-    size_t cap_c = 4096;
+    // candidate slots per query: k/f + the error band is the expectation; an overflowing batch is retried with 4x
+    size_t cap_c = std::max<size_t>(1024, 8 * k);
     if (const char *e = getenv("B200HNSW_BF_CAP")) cap_c = std::max(256, atoi(e));
+    cap_c = std::max(cap_c, tz.cap_floor);
     if (nq_pad > tz.q_cap || cap_c != tz.cap) {
         cudaFree(tz.qb); cudaFree(tz.qn2); cudaFree(tz.thr); cudaFree(tz.cand); cudaFree(tz.cand_cnt);
         tz.qb = nullptr; tz.qn2 = tz.thr = nullptr; tz.cand = tz.cand_cnt = nullptr; tz.q_cap = 0;
         B200_CUDA_OK(cudaMalloc(&tz.qb, nq_pad * kp * 2));
         B200_CUDA_OK(cudaMalloc(&tz.qn2, nq_pad * 4));
         B200_CUDA_OK(cudaMalloc(&tz.thr, nq_pad * 4));
+        cudaFree(tz.tabB); cudaFree(tz.tabT);
+        tz.tabB = tz.tabT = nullptr;
+        B200_CUDA_OK(cudaMalloc(&tz.tabB, nq_pad * 4));
+        B200_CUDA_OK(cudaMalloc(&tz.tabT, nq_pad * 4));
         B200_CUDA_OK(cudaMalloc(&tz.cand, nq_pad * cap_c * 4));
         B200_CUDA_OK(cudaMalloc(&tz.cand_cnt, nq_pad * 4));
         if (!tz.overflow) B200_CUDA_OK(cudaMalloc(&tz.overflow, 4));
@@ -479,7 +690,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     if (!rc) rc = make_map(&mB, tz.qb, nq_pad, kp, kGN);
     if (rc) return rc;
     GemmArgs a{};
-    a.xn2 = tz.xn2; a.qn2 = tz.qn2; a.thr = tz.thr; a.panelmin = tz.panelmin; a.cand = tz.cand; a.cand_cnt = tz.cand_cnt;
+    a.xn2 = tz.xn2; a.tabB = tz.tabB; a.tabT = tz.tabT; a.panelmin = tz.panelmin; a.cand = tz.cand; a.cand_cnt = tz.cand_cnt;
     a.n = (uint32_t)n; a.nq = (uint32_t)nq; a.nq_pad = (uint32_t)nq_pad; a.kchunks = (uint32_t)(kp / kGK);
     a.panels = (uint32_t)panels; a.qtiles = (uint32_t)(nq_pad / kGN); a.cap = (uint32_t)cap_c;
     static bool configured[16] = {};
@@ -488,21 +699,22 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        B200_CUDA_OK(cudaFuncSetAttribute(bf_rerank_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        B200_CUDA_OK(cudaFuncSetAttribute(bf_rerank_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured[device] = true;
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const bool ip = prm.metric == B200HNSW_IP;
     // pass 1: bounds from every stride-th panel
+    const unsigned tgrid = (unsigned)((nq_pad + 255) / 256);
+    bf_tables_kernel<<<tgrid, 256, 0, st>>>(tz.qn2, tz.thr, (uint32_t)nq_pad, ip ? 1 : 0, 0, tz.tabB, tz.tabT);
     a.stride = (uint32_t)stride;
     unsigned grid = (unsigned)std::min<size_t>((size_t)sms, sampled * a.qtiles);
     if (ip) bf_gemm_kernel<1, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
     else bf_gemm_kernel<0, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
-    bf_kth_kernel<<<(unsigned)((nq_pad + 127) / 128), 128, 0, st>>>(tz.panelmin, (uint32_t)sampled, (uint32_t)nq_pad,
-                                                                   (uint32_t)nq, (uint32_t)k, tz.thr);
+    bf_kth_kernel<<<(unsigned)(nq_pad / 32), 256, 0, st>>>(tz.panelmin, (uint32_t)sampled, (uint32_t)nq_pad,
+                                                          (uint32_t)nq, (uint32_t)k, tz.thr);
     // pass 2: candidates from all panels
+    bf_tables_kernel<<<tgrid, 256, 0, st>>>(tz.qn2, tz.thr, (uint32_t)nq_pad, ip ? 1 : 0, 1, tz.tabB, tz.tabT);
     a.stride = 1;
     grid = (unsigned)std::min<size_t>((size_t)sms, panels * a.qtiles);
     if (ip) bf_gemm_kernel<1, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
@@ -514,26 +726,33 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     else if (dim > 16) lane_floats = dim >> 4 << 4;
     else if (dim > 4) lane_floats = dim >> 2 << 2;
     else lane_floats = 0;
-    const size_t rsm = d4 * 16 + (cap_c + (cap_c & 1)) * 4 + cap_c * 8;
+    const size_t rsm = d4 * 16 + cap_c * 4 + (cap_c + (cap_c & 1)) * 4 + cap_c * 8 +
+                       std::max<size_t>((size_t)kRrRows * kRrStride, cap_c) * 4;
+    // |fast fp32 value - reference-order value| <= (longest add chain of either) * 2^-24 * sum|terms|, with slack
+    const float e2 = (float)((double)(dim / 4 + 64) * 1.2e-7);
     if (ip)
-        bf_rerank_kernel<1><<<(unsigned)nq, 256, rsm, st>>>(dX, dLabels, dQ_, (uint32_t)dim, (uint32_t)d4,
-                                                           (uint32_t)(lane_floats / 4), tz.cand, tz.cand_cnt,
-                                                           (uint32_t)cap_c, (uint32_t)k, (uint32_t)n, dl, dd, dc, tz.overflow);
+        launch_rerank<1>((uint32_t)d4, (unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim,
+                         (uint32_t)(lane_floats / 4), tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k, (uint32_t)n, e2,
+                         dl, dd, dc, tz.overflow);
     else
-        bf_rerank_kernel<0><<<(unsigned)nq, 256, rsm, st>>>(dX, dLabels, dQ_, (uint32_t)dim, (uint32_t)d4,
-                                                           (uint32_t)(lane_floats / 4), tz.cand, tz.cand_cnt,
-                                                           (uint32_t)cap_c, (uint32_t)k, (uint32_t)n, dl, dd, dc, tz.overflow);
+        launch_rerank<0>((uint32_t)d4, (unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim,
+                         (uint32_t)(lane_floats / 4), tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k, (uint32_t)n, e2,
+                         dl, dd, dc, tz.overflow);
     B200_CUDA_OK(cudaGetLastError());
     uint32_t ov = 0;
     B200_CUDA_OK(cudaMemcpyAsync(&ov, tz.overflow, 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
-    stats.kernel_launches += 5;
+    stats.kernel_launches += 8;
     if (getenv("B200HNSW_BF_STATS")) {  // diagnostic: candidates generated per batch (costs a D2H copy)
         std::vector<uint32_t> c(nq);
         B200_CUDA_OK(cudaMemcpy(c.data(), tz.cand_cnt, nq * 4, cudaMemcpyDeviceToHost));
         size_t tot = 0;
         for (uint32_t v : c) tot += v;
         tz.last_candidates = tot;
+    }
+    if (ov && cap_c < 16384) {  // rare: give every query 4x the slots and redo the batch on the tensor path
+        tz.cap_floor = cap_c * 4;
+        return search_tensor(dQ_, nq, k, dl, dd, dc, st);
     }
     return ov ? 1 : 0;
 }

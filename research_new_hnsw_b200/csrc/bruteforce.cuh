@@ -20,9 +20,9 @@ struct BruteTensor {
     void *xb = nullptr;        // bf16 [rows_pad][kp]
     float *xn2 = nullptr;      // [rows_pad] squared norms
     void *qb = nullptr;        // bf16 [q_cap][kp]
-    float *qn2 = nullptr, *thr = nullptr;
+    float *qn2 = nullptr, *thr = nullptr, *tabB = nullptr, *tabT = nullptr;
     uint32_t *panelmin = nullptr, *cand = nullptr, *cand_cnt = nullptr, *overflow = nullptr;
-    size_t kp = 0, rows_pad = 0, q_cap = 0, cap = 0, pm_elems = 0, last_candidates = 0;
+    size_t kp = 0, rows_pad = 0, q_cap = 0, cap = 0, cap_floor = 0, pm_elems = 0, last_candidates = 0;
     void release();
 };
 
