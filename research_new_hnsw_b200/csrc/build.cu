@@ -555,6 +555,7 @@ int HnswIndex::flush() {
     cudaEventDestroy(e1);
     dev.n = linked;
     mirror_dirty = true;
+    flags_dirty = true;
     return rc;
 }
 

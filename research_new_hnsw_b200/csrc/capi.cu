@@ -225,6 +225,7 @@ int b200hnsw_mark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:853-
     if (*f & 1) { set_error("The requested to delete element is already deleted"); return B200HNSW_E_STATE; }
     *f |= 1;
     m.num_deleted++;
+    h->ix.flags_dirty = true;
     return 0;
     B200_GUARD_END
 }
@@ -239,6 +240,7 @@ int b200hnsw_unmark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:89
     if (!(*f & 1)) { set_error("The requested to undelete element is not deleted"); return B200HNSW_E_STATE; }
     *f &= (unsigned char)~1;
     m.num_deleted--;
+    h->ix.flags_dirty = true;
     return 0;
     B200_GUARD_END
 }

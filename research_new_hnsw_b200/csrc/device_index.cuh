@@ -23,10 +23,11 @@ struct DeviceIndex {
     uint32_t *links0 = nullptr, *up_base = nullptr, *links_up = nullptr;
     uint64_t *labels = nullptr;
     uint32_t *err_flag = nullptr;
+    uint8_t *flags = nullptr;   // delete marks, allocated on first use
 
     void release() {
-        cudaFree(vec); cudaFree(links0); cudaFree(up_base); cudaFree(links_up); cudaFree(labels); cudaFree(err_flag);
-        vec = nullptr; links0 = up_base = links_up = nullptr; labels = nullptr; err_flag = nullptr;
+        cudaFree(vec); cudaFree(links0); cudaFree(up_base); cudaFree(links_up); cudaFree(labels); cudaFree(err_flag); cudaFree(flags);
+        vec = nullptr; links0 = up_base = links_up = nullptr; labels = nullptr; err_flag = nullptr; flags = nullptr;
         cap = n = 0;
     }
     size_t bytes() const {

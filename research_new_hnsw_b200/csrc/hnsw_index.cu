@@ -146,6 +146,18 @@ int HnswIndex::upload_all() {
     return upload_upper();
 }
 
+// delete marks (byte 2 of the level-0 record header, hnswalg.h:934-937) -> device byte array
+int HnswIndex::upload_flags() {
+    if (!flags_dirty && dev.flags) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    if (!dev.flags) B200_CUDA_OK(cudaMalloc(&dev.flags, std::max<size_t>(dev.cap, 1)));
+    std::vector<uint8_t> f(host.cur);
+    for (size_t i = 0; i < host.cur; i++) f[i] = host.deleted(i) ? 1 : 0;
+    if (host.cur) B200_CUDA_OK(cudaMemcpy(dev.flags, f.data(), host.cur, cudaMemcpyHostToDevice));
+    flags_dirty = false;
+    return 0;
+}
+
 int HnswIndex::ensure_scratch(size_t nq, size_t k) {
     if (nq <= scratch_q && k <= scratch_k) return 0;
     const size_t q = std::max(nq, scratch_q), kk = std::max(k, scratch_k);
@@ -185,39 +197,39 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
     return bits;
 }
 
-template <int TEAM, int LPV, int CPL, int METRIC>
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB>
 static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
     static bool configured[16] = {};  // per device; set once (benign race: idempotent)
     int d = 0;
     cudaGetDevice(&d);
     if (d < 16 && !configured[d]) {
         cudaFuncAttributes fa;
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC>));
+        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB>));
         int optin = 0;
         B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC>,
+        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
-    hnsw_search_kernel<TEAM, LPV, CPL, METRIC><<<a.nq, TEAM, smem, st>>>(a);
+    hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB><<<a.nq, TEAM, smem, st>>>(a);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int TEAM, int METRIC>
+template <int TEAM, int METRIC, bool NB = false>
 static int launch_team(const SearchArgs &a, size_t smem, cudaStream_t st) {
     const uint32_t d4 = a.d4;
-    if (d4 <= 8) return launch_one<TEAM, 8, 1, METRIC>(a, smem, st);
-    if (d4 <= 16) return launch_one<TEAM, 8, 2, METRIC>(a, smem, st);
-    if (d4 <= 24) return launch_one<TEAM, 8, 3, METRIC>(a, smem, st);
-    if (d4 <= 32) return launch_one<TEAM, 8, 4, METRIC>(a, smem, st);
-    if (d4 <= 48) return launch_one<TEAM, 16, 3, METRIC>(a, smem, st);
-    if (d4 <= 64) return launch_one<TEAM, 16, 4, METRIC>(a, smem, st);
-    if (d4 <= 96) return launch_one<TEAM, 32, 3, METRIC>(a, smem, st);
-    if (d4 <= 128) return launch_one<TEAM, 32, 4, METRIC>(a, smem, st);
-    if (d4 <= 192) return launch_one<TEAM, 32, 6, METRIC>(a, smem, st);
-    if (d4 <= 256) return launch_one<TEAM, 32, 8, METRIC>(a, smem, st);
+    if (d4 <= 8) return launch_one<TEAM, 8, 1, METRIC, NB>(a, smem, st);
+    if (d4 <= 16) return launch_one<TEAM, 8, 2, METRIC, NB>(a, smem, st);
+    if (d4 <= 24) return launch_one<TEAM, 8, 3, METRIC, NB>(a, smem, st);
+    if (d4 <= 32) return launch_one<TEAM, 8, 4, METRIC, NB>(a, smem, st);
+    if (d4 <= 48) return launch_one<TEAM, 16, 3, METRIC, NB>(a, smem, st);
+    if (d4 <= 64) return launch_one<TEAM, 16, 4, METRIC, NB>(a, smem, st);
+    if (d4 <= 96) return launch_one<TEAM, 32, 3, METRIC, NB>(a, smem, st);
+    if (d4 <= 128) return launch_one<TEAM, 32, 4, METRIC, NB>(a, smem, st);
+    if (d4 <= 192) return launch_one<TEAM, 32, 6, METRIC, NB>(a, smem, st);
+    if (d4 <= 256) return launch_one<TEAM, 32, 8, METRIC, NB>(a, smem, st);
     set_error("dimension > 1024 is not supported by the search kernel");
     return B200HNSW_E_UNSUPPORTED;
 }
@@ -245,11 +257,16 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
         set_error("search: null pointer or k == 0");
         return B200HNSW_E_ARG;
     }
-    if (host.num_deleted) {
-        set_error("search with deleted elements (non-bare-bone path, hnswalg.h:406-407) is not supported yet");
-        return B200HNSW_E_UNSUPPORTED;
-    }
     B200_CUDA_OK(cudaSetDevice(dev.device));
+    const bool nonbare = host.num_deleted != 0;  // hnswalg.h:1306: bare_bone_search = !num_deleted_ && !isIdAllowed
+    if (nonbare) {
+        if (linked >= (1u << 30)) {
+            set_error("search with deleted elements supports at most 2^30 elements");
+            return B200HNSW_E_UNSUPPORTED;
+        }
+        int rc = upload_flags();
+        if (rc) return rc;
+    }
     if (linked == 0) {  // hnswalg.h:1273: empty index -> empty result
         B200_CUDA_OK(cudaMemsetAsync(dl, 0xFF, nq * k * 8, st));
         fill_pad_rows(dd, dc, dw, nq, k, st);  // dist = +inf, counts = 0
@@ -268,14 +285,18 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.n = (uint32_t)linked; a.entry = dev_entry; a.maxlevel = dev_maxlevel;
     a.dim = (uint32_t)host.dim; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)host.maxM; a.maxM0 = (uint32_t)host.maxM0;
     a.nq = (uint32_t)nq; a.k = (uint32_t)k; a.ef = (uint32_t)efx;
-    const int team = pick_team(nq);
-    a.hash_bits = pick_hash_bits(efx, list_cap, team);
-    const SearchSmem L(a.ef, (uint32_t)list_cap, a.d4, a.hash_bits);
+    const int team = nonbare ? 128 : pick_team(nq);
+    a.flags = nonbare ? dev.flags : nullptr;
+    a.bufcap = (uint32_t)(nonbare ? 2 * efx : efx);
+    a.hash_bits = pick_hash_bits(a.bufcap, list_cap, team);
+    const SearchSmem L(a.bufcap, (uint32_t)list_cap, a.d4, a.hash_bits);
     if (L.total > 226 * 1024) {
         set_error("search configuration needs more than 226 KB of shared memory");
         return B200HNSW_E_UNSUPPORTED;
     }
     stats.kernel_launches += 1;
+    if (nonbare)
+        return prm.metric == B200HNSW_L2 ? launch_team<128, 0, true>(a, L.total, st) : launch_team<128, 1, true>(a, L.total, st);
     return prm.metric == B200HNSW_L2 ? launch_metric<0>(a, L.total, team, st) : launch_metric<1>(a, L.total, team, st);
 }
 

@@ -33,6 +33,7 @@ struct HnswIndex {
     uint32_t dev_entry = (uint32_t)-1;  // entry point / max level of the linked part of the graph
     int dev_maxlevel = -1;
     bool mirror_dirty = false;          // device link lists are newer than the host mirror
+    bool flags_dirty = true;            // delete marks changed since the last upload
     BuildScratch bld;
     // scratch for the host-pointer search path
     float *dQ = nullptr;
@@ -49,6 +50,7 @@ struct HnswIndex {
     int upload_all();                       // host mirror -> HBM (after load)
     int upload_upper();                     // rebuild up_base / links_up from the host mirror
     int ensure_scratch(size_t nq, size_t k);
+    int upload_flags();
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
                       uint32_t *dw, cudaStream_t st);
     int search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,

@@ -41,6 +41,8 @@ struct SearchArgs {
     float *out_dists;         // [nq][k]
     uint32_t *out_counts;     // [nq] or null
     uint32_t *out_work;       // [nq][4] or null: D, H0, Hup, resets
+    const uint8_t *flags;     // [n] bit 0 = deleted (hnswalg.h:934-937); null when nothing is deleted
+    uint32_t bufcap;          // entries per candidate buffer: ef (bare-bone) or 2*ef (deleted elements present)
     uint32_t n, entry;
     int32_t maxlevel;
     uint32_t dim, d4, maxM, maxM0;
@@ -51,10 +53,10 @@ struct SearchArgs {
 // shared-memory carve-up, shared by host (size) and device (pointers)
 struct SearchSmem {
     uint32_t off_buf0, off_buf1, off_acc, off_ids, off_dist, off_pref, off_q, off_hash, total;
-    __host__ __device__ SearchSmem(uint32_t ef, uint32_t list_cap, uint32_t d4, uint32_t hash_bits) {
+    __host__ __device__ SearchSmem(uint32_t bufcap, uint32_t list_cap, uint32_t d4, uint32_t hash_bits) {
         uint32_t o = 0;
-        off_buf0 = o; o += ef * 8;
-        off_buf1 = o; o += ef * 8;
+        off_buf0 = o; o += bufcap * 8;
+        off_buf1 = o; o += bufcap * 8;
         off_acc = o;  o += list_cap * 8;
         off_ids = o;  o += list_cap * 4;
         off_dist = o; o += list_cap * 4;
@@ -148,10 +150,10 @@ __device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *
 // Same gather as eval_list, fused with the admission test of searchBaseLayerST (hnswalg.h:395: size < ef ||
 // lowerBound > dist): the group leader appends the key of an admitted neighbour to acc[] (order irrelevant, the merge
 // ranks keys).
-template <int TEAM, int LPV, int CPL, int METRIC>
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false>
 __device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 *__restrict__ vec, uint32_t d4,
                                            const uint32_t *ids, int n, bool full, float bound, uint64_t *acc,
-                                           int *s_acc, int grp, int sub) {
+                                           int *s_acc, int grp, int sub, const uint8_t *__restrict__ flags = nullptr) {
     constexpr int NGRP = TEAM / LPV;
     const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
     for (int j = grp; j < n; j += 2 * NGRP) {
@@ -160,6 +162,11 @@ __device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 
         const uint32_t ida = ids[j], idb = ids[has2 ? j2 : j];
         const float4 *ra = vec + (size_t)ida * d4;
         const float4 *rb = vec + (size_t)idb * d4;
+        uint32_t dela = 0, delb = 0;  // deleted marks travel in bit 30 of the key (non-bare-bone search only)
+        if (NB && sub == 0) {
+            dela = (uint32_t)(__ldg(flags + ida) & 1u) << 30;
+            delb = (uint32_t)(__ldg(flags + idb) & 1u) << 30;
+        }
         float4 va[CPL], vb[CPL];
 #pragma unroll
         for (int c = 0; c < CPL; c++) {
@@ -184,8 +191,8 @@ __device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 
         float sb = group_sum<LPV>(pb.x + pb.y, gmask);
         if (METRIC == 1) { sa = 1.0f - sa; sb = 1.0f - sb; }
         if (sub == 0) {
-            if (!full || sa < bound) acc[atomicAdd(s_acc, 1)] = make_key(sa, ida);
-            if (has2 && (!full || sb < bound)) acc[atomicAdd(s_acc, 1)] = make_key(sb, idb);
+            if (!full || sa < bound) acc[atomicAdd(s_acc, 1)] = make_key(sa, ida | dela);
+            if (has2 && (!full || sb < bound)) acc[atomicAdd(s_acc, 1)] = make_key(sb, idb | delb);
         }
     }
 }
@@ -222,7 +229,7 @@ struct TeamCtx {
     float *dist;
     uint32_t *pref;   // neighbour list prefetched for the predicted next expansion
     uint32_t *hash;
-    int *s_cnt, *s_next, *s_best, *s_acc, *s_pref;
+    int *s_cnt, *s_next, *s_best, *s_acc, *s_pref, *s_size, *s_nr;
     uint32_t hash_bits;
     template <class Smem>
     __device__ __forceinline__ void bind(unsigned char *smem, const Smem &L, int *ints, uint32_t bits) {
@@ -234,10 +241,11 @@ struct TeamCtx {
         pref = (uint32_t *)(smem + L.off_pref);
         hash = (uint32_t *)(smem + L.off_hash);
         s_cnt = ints; s_next = ints + 1; s_best = ints + 2; s_acc = ints + 3; s_pref = ints + 4;
+        s_size = ints + 5; s_nr = ints + 6;
         hash_bits = bits;
     }
 };
-constexpr int kTeamInts = 5;
+constexpr int kTeamInts = 7;
 
 struct WorkCounters {
     uint32_t D = 0, H0 = 0, Hup = 0, resets = 0;
@@ -303,10 +311,19 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
 // Per hop (4 block barriers): [list of the node to expand: from the prefetch buffer when the prediction was right,
 // else one coalesced global read] -> visited filter + compaction -> gather + distance + admission (eval_admit)
 // while the last warp prefetches the list of the best other unexpanded entry -> rank merge.
-template <int TEAM, int LPV, int CPL, int METRIC>
+//
+// NB = true is the non-bare-bone variant (searchBaseLayerST<false>, hnswalg.h:324-433 without filter / stop condition):
+// deleted nodes are traversed but never enter top_candidates.  They stay in the same sorted buffer with bit 30 set;
+// only non-deleted entries count towards ef, the bound is the ef-th non-deleted distance, and everything behind that
+// entry is dropped after each merge (the reference would stop at the first such candidate, :346-358).  The buffer
+// holds up to 2*ef entries; more than ef deleted nodes inside the bound lose their farthest members.
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false>
 __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[CPL], const GraphView &g, int level,
                                            uint32_t ef, uint32_t cur, float curdist, int &cb, int &size,
-                                           WorkCounters &w) {
+                                           WorkCounters &w, const uint8_t *flags = nullptr, uint32_t bufcap = 0) {
+    constexpr uint32_t IDM = NB ? 0x3FFFFFFFu : kIdMask;
+    constexpr uint64_t KM = NB ? 0xFFFFFFFF3FFFFFFFull : kKeyMask;
+    const uint32_t cap = NB ? bufcap : ef;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = tid % LPV, grp = tid / LPV;
     const uint32_t HS = 1u << c.hash_bits;
@@ -314,8 +331,10 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
     const bool can_pref = llen <= 64;  // the prefetching warp holds the list in two registers per lane
     cb = 0;
     size = 1;
+    const uint32_t ep_del = NB ? (uint32_t)(__ldg(flags + cur) & 1u) : 0u;
+    int nr = ep_del ? 0 : 1;  // non-deleted entries in the buffer (NB only; uniform)
     if (tid == 0) {
-        c.buf_a[0] = make_key(curdist, cur);
+        c.buf_a[0] = make_key(curdist, cur | (ep_del << 30));
         hash_insert(c.hash, c.hash_bits, cur);
         *c.s_next = 0;
         *c.s_pref = -1;
@@ -328,9 +347,9 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
         const int next = *c.s_next;
         if (next >= size) break;
         uint64_t *src = cb ? c.buf_b : c.buf_a, *dst = cb ? c.buf_a : c.buf_b;
-        const uint32_t node = (uint32_t)src[next] & kIdMask;
-        const bool full = (uint32_t)size == ef;
-        const float bound = full ? ord2f((uint32_t)(src[ef - 1] >> 32)) : 3.402823466e+38f;
+        const uint32_t node = (uint32_t)src[next] & IDM;
+        const bool full = NB ? (uint32_t)nr == ef : (uint32_t)size == ef;
+        const float bound = full ? ord2f((uint32_t)(src[size - 1] >> 32)) : 3.402823466e+38f;
         const uint32_t *lst = g.list(node, level);
         const bool hit = can_pref && node == pref_node;
         // issue the list read before the barrier so its latency overlaps the bookkeeping
@@ -341,7 +360,7 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
             __syncthreads();
             for (uint32_t i = tid; i < HS; i += TEAM) c.hash[i] = kEmpty;
             __syncthreads();
-            for (int i = tid; i < size; i += TEAM) hash_insert(c.hash, c.hash_bits, (uint32_t)src[i] & kIdMask);
+            for (int i = tid; i < size; i += TEAM) hash_insert(c.hash, c.hash_bits, (uint32_t)src[i] & IDM);
             hcount = size;
             w.resets += 1;
         }
@@ -373,7 +392,7 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
             const bool un = pos < size && !((uint32_t)src[pos] & kExpanded);
             const uint32_t b = __ballot_sync(0xffffffffu, un);
             if (b) {
-                pnode = (uint32_t)src[next + __ffs(b)] & kIdMask;
+                pnode = (uint32_t)src[next + __ffs(b)] & IDM;
                 const uint32_t *pl = g.list(pnode, level);
                 if ((uint32_t)lane < llen) pf0 = __ldg(pl + lane);
                 if ((uint32_t)lane + 32 < llen) pf1 = __ldg(pl + lane + 32);
@@ -384,7 +403,7 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
         w.H0 += 1;
         w.D += nnew;
         hcount += nnew;
-        eval_admit<TEAM, LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, nnew, full, bound, c.acc, c.s_acc, grp, sub);
+        eval_admit<TEAM, LPV, CPL, METRIC, NB>(q, g.vec, g.d4, c.ids, nnew, full, bound, c.acc, c.s_acc, grp, sub, flags);
         if (can_pref && warp == TEAM / 32 - 1) {
             if ((uint32_t)lane < llen) c.pref[lane] = pf0;
             if ((uint32_t)lane + 32 < llen) c.pref[lane + 32] = pf1;
@@ -402,30 +421,31 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
             // merge by rank: final position = own index + number of smaller keys in the other list
             for (int i = tid; i < size; i += TEAM) {
                 const uint64_t key = src[i];
-                const uint64_t km = key & kKeyMask;
+                const uint64_t km = key & KM;
                 int pos = i;
-                for (int j = 0; j < m; j++) pos += (c.acc[j] < km) ? 1 : 0;
-                if ((uint32_t)pos < ef) {
+                for (int j = 0; j < m; j++) pos += ((c.acc[j] & KM) < km) ? 1 : 0;
+                if ((uint32_t)pos < cap) {
                     dst[pos] = key;
                     if (!((uint32_t)key & kExpanded)) local_min = min(local_min, pos);
                 }
             }
             for (int j = TEAM - 1 - tid; j < m; j += TEAM) {
                 const uint64_t key = c.acc[j];
+                const uint64_t km = key & KM;
                 int r = 0;
-                for (int i = 0; i < m; i++) r += (c.acc[i] < key) ? 1 : 0;
+                for (int i = 0; i < m; i++) r += ((c.acc[i] & KM) < km) ? 1 : 0;
                 int lo = 0, hi = size;  // upper bound: equal keys (impossible by construction) stay distinct
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if ((src[mid] & kKeyMask) <= key) lo = mid + 1; else hi = mid;
+                    if ((src[mid] & KM) <= km) lo = mid + 1; else hi = mid;
                 }
                 const int pos = r + lo;
-                if ((uint32_t)pos < ef) {
+                if ((uint32_t)pos < cap) {
                     dst[pos] = key;
                     local_min = min(local_min, pos);
                 }
             }
-            size = min((int)ef, size + m);
+            size = min((int)cap, size + m);
             cb ^= 1;
         }
 #pragma unroll
@@ -433,14 +453,37 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
         if (lane == 0 && local_min != 0x7fffffff) atomicMin(c.s_next, local_min);
         if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; }
         __syncthreads();  // (D) merged buffer and s_next visible
+        if (NB && m != 0) {
+            // cut the buffer behind the ef-th non-deleted entry (the new lowerBound); one warp scans 32 keys a step
+            if (warp == 0) {
+                const uint64_t *buf = cb ? c.buf_b : c.buf_a;
+                int seen = 0, cut = size;
+                for (int b0 = 0; b0 < size; b0 += 32) {
+                    const int i = b0 + lane;
+                    const bool live = i < size && !((uint32_t)buf[i] & 0x40000000u);
+                    const uint32_t bm = __ballot_sync(0xffffffffu, live);
+                    const int cntb = __popc(bm);
+                    if (seen + cntb >= (int)ef) {
+                        cut = b0 + (int)__fns(bm, 0, (int)ef - seen) + 1;
+                        seen = (int)ef;
+                        break;
+                    }
+                    seen += cntb;
+                }
+                if (lane == 0) { *c.s_size = cut; *c.s_nr = seen; }
+            }
+            __syncthreads();
+            size = *c.s_size;
+            nr = *c.s_nr;
+        }
     }
 }
 
-template <int TEAM, int LPV, int CPL, int METRIC>
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false>
 __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hnsw_search_kernel(const SearchArgs p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
-    const SearchSmem L(p.ef, list_cap, p.d4, p.hash_bits);
+    const SearchSmem L(p.bufcap, list_cap, p.d4, p.hash_bits);
     __shared__ int s_ints[kTeamInts];
     TeamCtx c;
     c.bind(smem, L, s_ints, p.hash_bits);
@@ -479,16 +522,34 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
 
     // ---- searchBaseLayerST on level 0 ----
     int cb, size;
-    beam_level<TEAM, LPV, CPL, METRIC>(c, q, g, 0, p.ef, cur, curdist, cb, size, w);
+    beam_level<TEAM, LPV, CPL, METRIC, NB>(c, q, g, 0, p.ef, cur, curdist, cb, size, w, p.flags, p.bufcap);
 
     // ---- epilogue: first k entries are the result, closest first (hnswalg.h:1315-1322) ----
     const uint64_t *res = cb ? c.buf_b : c.buf_a;
+    if (NB) {
+        // results are the non-deleted entries only: compact them to the front (same buffer, other half as scratch)
+        uint64_t *tmp = cb ? c.buf_a : c.buf_b;
+        if (tid < 32) {
+            int outn = 0;
+            for (int b0 = 0; b0 < size; b0 += 32) {
+                const int i = b0 + tid;
+                const bool live = i < size && !((uint32_t)res[i] & 0x40000000u);
+                const uint32_t bm = __ballot_sync(0xffffffffu, live);
+                if (live) tmp[outn + __popc(bm & ((1u << tid) - 1u))] = res[i];
+                outn += __popc(bm);
+            }
+            if (tid == 0) *c.s_size = outn;
+        }
+        __syncthreads();
+        res = tmp;
+        size = *c.s_size;
+    }
     for (uint32_t j = tid; j < p.k; j += TEAM) {
         uint64_t lab = 0xFFFFFFFFFFFFFFFFull;
         float dj = __int_as_float(0x7f800000);
         if (j < (uint32_t)size) {
             const uint64_t key = res[j];
-            lab = __ldg(p.labels + ((uint32_t)key & kIdMask));
+            lab = __ldg(p.labels + ((uint32_t)key & (NB ? 0x3FFFFFFFu : kIdMask)));
             dj = ord2f((uint32_t)(key >> 32));
         }
         p.out_labels[(size_t)qi * p.k + j] = lab;

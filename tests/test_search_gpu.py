@@ -150,3 +150,33 @@ def test_merge_topk_kernel_matches_reference_semantics(lib):
         gl, gd = cuda_merge()(torch.from_numpy(L.view(np.int64)).cuda(), torch.from_numpy(D).cuda(), k)
         torch.cuda.synchronize()
         assert np.array_equal(gl.cpu().numpy().view(np.uint64), el) and np.array_equal(gd.cpu().numpy(), ed)
+
+
+@pytest.mark.parametrize("name,frac", [("l2_d128", 0.05), ("ip_d96", 0.2), ("lowrank_d128", 0.5)])
+def test_deleted_elements_non_bare_search(lib, orc, graphs, name, frac):
+    """markDelete -> searchBaseLayerST<false> (hnswalg.h:324-433): deleted nodes are traversed, never returned."""
+    s = graphs[name]
+    idx = lib.HierarchicalNSW(_space(lib, s["metric"], s["d"]), s["path"])
+    cpu = orc.hnsw_load(s["metric"], s["d"], s["path"])
+    dead = np.random.default_rng(9).choice(s["n"], int(frac * s["n"]), replace=False)
+    for l in dead.tolist():
+        idx.markDelete(l)
+        cpu.mark_delete(l)
+    assert idx.getDeletedCount() == len(dead)
+    dead_set = set(dead.tolist())
+    for ef in (16, 64, 128):
+        r = idx.searchKnnBatch(s["Q"], 10, ef=ef)
+        c = cpu.search(s["Q"], 10, ef)
+        assert not (set(r["labels"].ravel().tolist()) & dead_set)
+        same = _same_sets(r["labels"], c["labels"]).mean()
+        if frac <= 0.2:
+            _check(r, c, (name, ef, "deleted"))
+        else:  # more deleted nodes than the 2*ef buffer can carry inside the bound: documented approximation
+            assert same >= 0.9, (name, ef, same)
+    with pytest.raises(lib.B200Error, match="already deleted"):
+        idx.markDelete(int(dead[0]))
+    for l in dead.tolist():
+        idx.unmarkDelete(l)
+    assert idx.getDeletedCount() == 0
+    bare = orc.hnsw_load(s["metric"], s["d"], s["path"]).search(s["Q"], 10, 64)
+    _check(idx.searchKnnBatch(s["Q"], 10, ef=64), bare, (name, "undeleted"))
