@@ -56,3 +56,42 @@ def test_reference_index_builder_end_to_end(orc, ref, tmp_path):
         r_gpu_graph = rec(back.search(Q, 10, 200)["labels"])
         r_cpu_graph = rec(cpu.search(Q, 10, 200)["labels"])
         assert r_gpu_graph >= r_cpu_graph - 0.01, (r_gpu_graph, r_cpu_graph)
+
+
+def test_reference_hnsw_service_over_http(orc, tmp_path):
+    """hnsw_service/main.cpp:49-96 (normal mode) unchanged: loadIndex + POST /search -> setEf + searchKnn, results
+    furthest first (main.cpp:71-75).  RLIMIT_AS (main.cpp:19-22) is lifted by the preload shim."""
+    import json
+    import socket
+    import time
+    import urllib.request
+    exe = _need("hnsw_service")
+    n, d = 5000, 128
+    X = np.random.default_rng(3).standard_normal((n, d), dtype=np.float32)
+    cpu = orc.hnsw_new(bind.L2, d, n, 16, 100)
+    cpu.add(X)
+    g = str(tmp_path / "svc.bin")
+    cpu.save(g)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, LD_PRELOAD=os.path.join(ROOT, "research_new_hnsw_b200", "libb200_norlimit.so"))
+    p = subprocess.Popen([exe, "--graph", g, "--port", str(port), "--dim", str(d)], env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, text=True)
+    try:
+        for _ in range(200):
+            try:
+                info = json.load(urllib.request.urlopen("http://127.0.0.1:%d/info" % port, timeout=1))
+                break
+            except Exception:
+                assert p.poll() is None, p.stderr.read()
+                time.sleep(0.1)
+        assert info["nodes"] == n and info["dim"] == d
+        Q = np.random.default_rng(4).standard_normal((20, d), dtype=np.float32)
+        want = cpu.search(Q, 5, 64)
+        for i in range(len(Q)):
+            body = json.dumps({"query": Q[i].tolist(), "k": 5, "ef": 64}).encode()
+            req = urllib.request.Request("http://127.0.0.1:%d/search" % port, data=body)
+            res = json.load(urllib.request.urlopen(req, timeout=10))["results"]
+            assert [r["id"] for r in res] == want["labels"][i][::-1].tolist()      # furthest first
+            assert np.allclose([r["distance"] for r in res], want["dists"][i][::-1], rtol=1e-5)
+    finally:
+        p.kill()
