@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--recall", type=float, default=0.95)
     ap.add_argument("--batches", type=int, default=4, help="distinct query batches cycled through the steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
+                    help="device copy of the vectors: f32 (default, reference-exact traversal) or bf16 traversal + f32 re-rank")
     return ap.parse_args()
 
 
@@ -130,10 +132,18 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
-def algorithmic_bytes(a, work):
-    """B_q = D*d*4 + H0*(4+4*maxM0) + Hup*(4+4*maxM) + 4d + 12k, summed over the batch (counted)."""
+def algorithmic_bytes(a, work, ef=0):
+    """B_q = D*d*s + H0*(4+4*maxM0) + Hup*(4+4*maxM) + 4d + 12k, summed over the batch (counted).
+    s = 4 (f32 rows); with bf16 storage the traversal reads 2-byte components and the final ef entries are re-read
+    as f32 rows (the kernel's D counts both)."""
     D, H0, Hup = int(work[:, 0].sum()), int(work[:, 1].sum()), int(work[:, 2].sum())
-    return D * a.dim * 4 + H0 * (4 + 8 * a.M) + Hup * (4 + 4 * a.M) + work.shape[0] * (4 * a.dim + 12 * a.k), D, H0, Hup
+    nq = work.shape[0]
+    if a.storage == "bf16":
+        rer = min(ef, D // max(nq, 1)) * nq
+        vec_bytes = (D - rer) * a.dim * 2 + rer * a.dim * 4
+    else:
+        vec_bytes = D * a.dim * 4
+    return vec_bytes + H0 * (4 + 8 * a.M) + Hup * (4 + 4 * a.M) + nq * (4 * a.dim + 12 * a.k), D, H0, Hup
 
 
 def peaks():
@@ -232,7 +242,7 @@ def run_b200(a, rank, local_rank, world):
         # the graph both arms search: built by the reference on the host cores, loaded from its saveIndex file
         path, build_s = build_graph_with_reference(a, rank, X, threads)
         t0 = time.time()
-        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), path, device=local_rank)
+        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), path, device=local_rank, storage=1 if a.storage == "bf16" else 0)
         load_s = time.time() - t0
         graph_note = "reference-built saveIndex file%s, loaded in %.1f s" % (
             "" if build_s == 0 else " (%.1f s, %.0f points/s on %d threads)" % (build_s, a.n / build_s, threads), load_s)
@@ -240,7 +250,8 @@ def run_b200(a, rank, local_rank, world):
         # one sub-index per GPU, built on that GPU (batched addPoint, csrc/build.cu)
         path = None
         t0 = time.time()
-        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), a.n, a.M, a.efc, device=local_rank)
+        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), a.n, a.M, a.efc, device=local_rank,
+                                  storage=1 if a.storage == "bf16" else 0)
         idx.addPoints(X, shard_labels)
         idx.flush()
         build_s = time.time() - t0
@@ -370,7 +381,7 @@ def run_b200(a, rank, local_rank, world):
     del X
 
     if rank == 0:
-        bytes_sum = [algorithmic_bytes(a, w) for w in works]
+        bytes_sum = [algorithmic_bytes(a, w, ef) for w in works]
         per_launch = float(np.mean([b[0] for b in bytes_sum]))
         peak, peak_src = peaks()
         achieved = per_launch / (kernel_ms * 1e-3) / 1e9
@@ -393,8 +404,9 @@ def run_b200(a, rank, local_rank, world):
             "metric": "QPS @ recall@10>=0.95, 1Mx128 L2", "value": world * a.nq * a.steps / (ms_total * 1e-3),
             "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if a.storage == "f32" else "f32 accumulate over bf16 rows, f32 re-rank", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
+                       "storage": a.storage,
                        "parallelism": "1 GPU" if world == 1 else
                        "shard%d: one %d-point sub-index per GPU, queries replicated, NCCL all_gather + GPU merge; value "
                        "counts shard-level searches (merged queries/s = value/%d)" % (world, a.n, world),

@@ -419,6 +419,10 @@ int HnswIndex::flush() {
         }
         cudaFree(raw);
     }
+    {
+        int rc16 = sync_bf16(linked, n_new);
+        if (rc16) return rc16;
+    }
     // ---- upper-level list slots of the staged points (appended after the existing ones) ----
     {
         std::vector<uint32_t> base(n_new, kEmpty);

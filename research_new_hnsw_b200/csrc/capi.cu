@@ -32,10 +32,7 @@ static int check_params(const b200hnsw_params *p) {
     if (!p) { set_error("params is null"); return B200HNSW_E_ARG; }
     if (p->dim == 0) { set_error("dim must be > 0"); return B200HNSW_E_ARG; }
     if (p->metric != B200HNSW_L2 && p->metric != B200HNSW_IP) { set_error("unknown metric"); return B200HNSW_E_ARG; }
-    if (p->storage != B200HNSW_F32) {
-        set_error("bf16 storage variant is not available in this build");
-        return B200HNSW_E_UNSUPPORTED;
-    }
+    if (p->storage != B200HNSW_F32 && p->storage != B200HNSW_BF16) { set_error("unknown storage type"); return B200HNSW_E_ARG; }
     return 0;
 }
 

@@ -24,10 +24,12 @@ struct DeviceIndex {
     uint64_t *labels = nullptr;
     uint32_t *err_flag = nullptr;
     uint8_t *flags = nullptr;   // delete marks, allocated on first use
+    uint4 *vec16 = nullptr;     // bf16 copy of the vectors [cap][d16] (storage variant B200HNSW_BF16)
+    size_t d16 = 0;
 
     void release() {
-        cudaFree(vec); cudaFree(links0); cudaFree(up_base); cudaFree(links_up); cudaFree(labels); cudaFree(err_flag); cudaFree(flags);
-        vec = nullptr; links0 = up_base = links_up = nullptr; labels = nullptr; err_flag = nullptr; flags = nullptr;
+        cudaFree(vec); cudaFree(links0); cudaFree(up_base); cudaFree(links_up); cudaFree(labels); cudaFree(err_flag); cudaFree(flags); cudaFree(vec16);
+        vec = nullptr; links0 = up_base = links_up = nullptr; labels = nullptr; err_flag = nullptr; flags = nullptr; vec16 = nullptr;
         cap = n = 0;
     }
     size_t bytes() const {
@@ -60,6 +62,24 @@ static __global__ void deinterleave_kernel(const uint32_t *__restrict__ raw, siz
     for (uint32_t j = lane; j < d4 * 4; j += 32)
         vec[(size_t)id * d4 * 4 + j] = j < dim ? __uint_as_float(rv[j]) : 0.f;
     if (lane == 0) labels[id] = (uint64_t)rv[dim] | ((uint64_t)rv[dim + 1] << 32);
+}
+
+// fp32 rows -> bf16 rows (round to nearest even), 8 elements per 128-bit chunk, zero padded.  One thread per chunk.
+static __global__ void rows_to_bf16_kernel(const float4 *__restrict__ vec, uint32_t d4, uint32_t d16, uint32_t first,
+                                           uint32_t count, uint4 *__restrict__ vec16) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)count * d16) return;
+    const uint32_t r = first + (uint32_t)(i / d16), c = (uint32_t)(i % d16);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (2 * c < d4) a = vec[(size_t)r * d4 + 2 * c];
+    if (2 * c + 1 < d4) b = vec[(size_t)r * d4 + 2 * c + 1];
+    auto pack = [](float lo, float hi) -> uint32_t {
+        uint32_t l = __float_as_uint(lo), h = __float_as_uint(hi);
+        l = (l + 0x7FFFu + ((l >> 16) & 1u)) >> 16;
+        h = (h + 0x7FFFu + ((h >> 16) & 1u)) >> 16;
+        return l | (h << 16);
+    };
+    vec16[(size_t)r * d16 + c] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
 }
 
 }  // namespace b200

@@ -57,6 +57,22 @@ int HnswIndex::alloc_device(size_t cap) {
     B200_CUDA_OK(cudaMemset(dev.err_flag, 0, 4));
     B200_CUDA_OK(cudaMemset(dev.up_base, 0xFF, c * 4));
     B200_CUDA_OK(cudaMemset(dev.links0, 0xFF, c * dev.maxM0 * 4));
+    if (prm.storage == B200HNSW_BF16) {
+        dev.d16 = (host.dim + 7) / 8;
+        B200_CUDA_OK(cudaMalloc(&dev.vec16, c * dev.d16 * 16));
+    }
+    return 0;
+}
+
+// refresh the bf16 copy of rows [first, first+count) from the fp32 rows already in HBM
+int HnswIndex::sync_bf16(size_t first, size_t count) {
+    if (prm.storage != B200HNSW_BF16 || !count) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    const size_t tot = count * dev.d16;
+    rows_to_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(dev.vec, (uint32_t)dev.d4, (uint32_t)dev.d16, (uint32_t)first,
+                                                              (uint32_t)count, dev.vec16);
+    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -143,6 +159,8 @@ int HnswIndex::upload_all() {
     dev_entry = host.enterpoint;
     dev_maxlevel = host.maxlevel;
     mirror_dirty = false;
+    int rc16 = sync_bf16(0, n);
+    if (rc16) return rc16;
     return upload_upper();
 }
 
@@ -197,39 +215,39 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
     return bits;
 }
 
-template <int TEAM, int LPV, int CPL, int METRIC, bool NB>
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB, int STORE>
 static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
     static bool configured[16] = {};  // per device; set once (benign race: idempotent)
     int d = 0;
     cudaGetDevice(&d);
     if (d < 16 && !configured[d]) {
         cudaFuncAttributes fa;
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB>));
+        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE>));
         int optin = 0;
         B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB>,
+        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
-    hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB><<<a.nq, TEAM, smem, st>>>(a);
+    hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE><<<a.nq, TEAM, smem, st>>>(a);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int TEAM, int METRIC, bool NB = false>
+template <int TEAM, int METRIC, bool NB = false, int STORE = 0>
 static int launch_team(const SearchArgs &a, size_t smem, cudaStream_t st) {
     const uint32_t d4 = a.d4;
-    if (d4 <= 8) return launch_one<TEAM, 8, 1, METRIC, NB>(a, smem, st);
-    if (d4 <= 16) return launch_one<TEAM, 8, 2, METRIC, NB>(a, smem, st);
-    if (d4 <= 24) return launch_one<TEAM, 8, 3, METRIC, NB>(a, smem, st);
-    if (d4 <= 32) return launch_one<TEAM, 8, 4, METRIC, NB>(a, smem, st);
-    if (d4 <= 48) return launch_one<TEAM, 16, 3, METRIC, NB>(a, smem, st);
-    if (d4 <= 64) return launch_one<TEAM, 16, 4, METRIC, NB>(a, smem, st);
-    if (d4 <= 96) return launch_one<TEAM, 32, 3, METRIC, NB>(a, smem, st);
-    if (d4 <= 128) return launch_one<TEAM, 32, 4, METRIC, NB>(a, smem, st);
-    if (d4 <= 192) return launch_one<TEAM, 32, 6, METRIC, NB>(a, smem, st);
-    if (d4 <= 256) return launch_one<TEAM, 32, 8, METRIC, NB>(a, smem, st);
+    if (d4 <= 8) return launch_one<TEAM, 8, 1, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 16) return launch_one<TEAM, 8, 2, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 24) return launch_one<TEAM, 8, 3, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 32) return launch_one<TEAM, 8, 4, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 48) return launch_one<TEAM, 16, 3, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 64) return launch_one<TEAM, 16, 4, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 96) return launch_one<TEAM, 32, 3, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 128) return launch_one<TEAM, 32, 4, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 192) return launch_one<TEAM, 32, 6, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 256) return launch_one<TEAM, 32, 8, METRIC, NB, STORE>(a, smem, st);
     set_error("dimension > 1024 is not supported by the search kernel");
     return B200HNSW_E_UNSUPPORTED;
 }
@@ -285,7 +303,11 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.n = (uint32_t)linked; a.entry = dev_entry; a.maxlevel = dev_maxlevel;
     a.dim = (uint32_t)host.dim; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)host.maxM; a.maxM0 = (uint32_t)host.maxM0;
     a.nq = (uint32_t)nq; a.k = (uint32_t)k; a.ef = (uint32_t)efx;
-    const int team = nonbare ? 128 : pick_team(nq);
+    int team = nonbare ? 128 : pick_team(nq);
+    if (prm.storage == B200HNSW_BF16 && team == 32) team = 64;
+    const bool bf16 = prm.storage == B200HNSW_BF16 && !nonbare;  // deleted elements: fp32 rows (non-bare kernel)
+    a.vec16 = bf16 ? dev.vec16 : nullptr;
+    a.d16 = (uint32_t)dev.d16;
     a.flags = nonbare ? dev.flags : nullptr;
     a.bufcap = (uint32_t)(nonbare ? 2 * efx : efx);
     a.hash_bits = pick_hash_bits(a.bufcap, list_cap, team);
@@ -297,6 +319,11 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     stats.kernel_launches += 1;
     if (nonbare)
         return prm.metric == B200HNSW_L2 ? launch_team<128, 0, true>(a, L.total, st) : launch_team<128, 1, true>(a, L.total, st);
+    if (bf16) {
+        if (team == 64)
+            return prm.metric == B200HNSW_L2 ? launch_team<64, 0, false, 1>(a, L.total, st) : launch_team<64, 1, false, 1>(a, L.total, st);
+        return prm.metric == B200HNSW_L2 ? launch_team<128, 0, false, 1>(a, L.total, st) : launch_team<128, 1, false, 1>(a, L.total, st);
+    }
     return prm.metric == B200HNSW_L2 ? launch_metric<0>(a, L.total, team, st) : launch_metric<1>(a, L.total, team, st);
 }
 

@@ -51,6 +51,7 @@ struct HnswIndex {
     int upload_upper();                     // rebuild up_base / links_up from the host mirror
     int ensure_scratch(size_t nq, size_t k);
     int upload_flags();
+    int sync_bf16(size_t first, size_t count);
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
                       uint32_t *dw, cudaStream_t st);
     int search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,

@@ -42,6 +42,8 @@ struct SearchArgs {
     uint32_t *out_counts;     // [nq] or null
     uint32_t *out_work;       // [nq][4] or null: D, H0, Hup, resets
     const uint8_t *flags;     // [n] bit 0 = deleted (hnswalg.h:934-937); null when nothing is deleted
+    const uint4 *vec16;       // [n][d16] bf16 rows (storage variant) or null
+    uint32_t d16;
     uint32_t bufcap;          // entries per candidate buffer: ef (bare-bone) or 2*ef (deleted elements present)
     uint32_t n, entry;
     int32_t maxlevel;
@@ -197,6 +199,70 @@ __device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 
     }
 }
 
+// bf16 storage variant of the gather: rows are 128-bit chunks of 8 bf16, the query stays fp32 in registers (two
+// float4 per chunk), accumulation is fp32 (FFMA2).  Four rows in flight per group carry the same bytes as two fp32
+// rows, so a hop needs half as many dependent round trips.
+template <int METRIC>
+__device__ __forceinline__ float2 acc8(float2 acc, const float4 &qa, const float4 &qb, const uint4 &v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const float2 qp[4] = {make_float2(qa.x, qa.y), make_float2(qa.z, qa.w), make_float2(qb.x, qb.y), make_float2(qb.z, qb.w)};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float2 e = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+        if (METRIC == 0) {
+            const float2 d = __ffma2_rn(e, make_float2(-1.f, -1.f), qp[i]);
+            acc = __ffma2_rn(d, d, acc);
+        } else {
+            acc = __ffma2_rn(qp[i], e, acc);
+        }
+    }
+    return acc;
+}
+
+template <int TEAM, int LPV, int C16, int METRIC>
+__device__ __forceinline__ void eval_admit_bf16(const float4 (&q)[C16][2], const uint4 *__restrict__ vec16, uint32_t d16,
+                                                const uint32_t *ids, int n, bool full, float bound, uint64_t *acc,
+                                                int *s_acc, int grp, int sub) {
+    constexpr int NGRP = TEAM / LPV;
+    constexpr int ROWS = 4;
+    const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
+    for (int j = grp; j < n; j += ROWS * NGRP) {
+        uint32_t id[ROWS];
+        bool has[ROWS];
+        uint4 v[ROWS][C16];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            const int jr = j + r * NGRP;
+            has[r] = jr < n;
+            id[r] = ids[has[r] ? jr : j];
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++)
+#pragma unroll
+            for (int c = 0; c < C16; c++) {
+                const uint32_t idx = sub + c * LPV;
+                v[r][c] = (has[r] && idx < d16) ? ldg_stream_u4(vec16 + (size_t)id[r] * d16 + idx) : make_uint4(0, 0, 0, 0);
+            }
+        float2 p[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) p[r] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C16; c++) {
+            const uint32_t idx = sub + c * LPV;
+            if (idx < d16) {
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) p[r] = acc8<METRIC>(p[r], q[c][0], q[c][1], v[r][c]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+            float sr = group_sum<LPV>(p[r].x + p[r].y, gmask);
+            if (METRIC == 1) sr = 1.0f - sr;
+            if (sub == 0 && has[r] && (!full || sr < bound)) acc[atomicAdd(s_acc, 1)] = make_key(sr, id[r]);
+        }
+    }
+}
+
 __device__ __forceinline__ bool hash_insert(uint32_t *tab, uint32_t bits, uint32_t id) {
     const uint32_t mask = (1u << bits) - 1u;
     uint32_t h = (id * 0x9E3779B1u) >> (32 - bits);
@@ -215,6 +281,8 @@ struct GraphView {
     const uint32_t *up_base;  // [n]
     const uint32_t *links_up; // [lists][maxM]
     uint32_t d4, maxM, maxM0;
+    const uint4 *vec16 = nullptr;  // optional bf16 copy [n][d16], 8 elements per 128-bit chunk (storage variant)
+    uint32_t d16 = 0;
     __device__ __forceinline__ const uint32_t *list(uint32_t node, int level) const {
         return level == 0 ? links0 + (size_t)node * maxM0
                           : links_up + ((size_t)__ldg(up_base + node) + (uint32_t)(level - 1)) * maxM;
@@ -317,10 +385,11 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
 // only non-deleted entries count towards ef, the bound is the ef-th non-deleted distance, and everything behind that
 // entry is dropped after each merge (the reference would stop at the first such candidate, :346-358).  The buffer
 // holds up to 2*ef entries; more than ef deleted nodes inside the bound lose their farthest members.
-template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false>
-__device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[CPL], const GraphView &g, int level,
-                                           uint32_t ef, uint32_t cur, float curdist, int &cb, int &size,
-                                           WorkCounters &w, const uint8_t *flags = nullptr, uint32_t bufcap = 0) {
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false, int STORE = 0>
+__device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[STORE ? (CPL + 1) / 2 * 2 : CPL],
+                                           const GraphView &g, int level, uint32_t ef, uint32_t cur, float curdist,
+                                           int &cb, int &size, WorkCounters &w, const uint8_t *flags = nullptr,
+                                           uint32_t bufcap = 0) {
     constexpr uint32_t IDM = NB ? 0x3FFFFFFFu : kIdMask;
     constexpr uint64_t KM = NB ? 0xFFFFFFFF3FFFFFFFull : kKeyMask;
     const uint32_t cap = NB ? bufcap : ef;
@@ -403,7 +472,14 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
         w.H0 += 1;
         w.D += nnew;
         hcount += nnew;
-        eval_admit<TEAM, LPV, CPL, METRIC, NB>(q, g.vec, g.d4, c.ids, nnew, full, bound, c.acc, c.s_acc, grp, sub, flags);
+        if (STORE == 0) {
+            eval_admit<TEAM, LPV, CPL, METRIC, NB>(reinterpret_cast<const float4(&)[CPL]>(q), g.vec, g.d4, c.ids, nnew, full,
+                                                   bound, c.acc, c.s_acc, grp, sub, flags);
+        } else {
+            constexpr int C16 = (CPL + 1) / 2;
+            eval_admit_bf16<TEAM, LPV, C16, METRIC>(reinterpret_cast<const float4(&)[C16][2]>(q), g.vec16, g.d16, c.ids, nnew,
+                                                    full, bound, c.acc, c.s_acc, grp, sub);
+        }
         if (can_pref && warp == TEAM / 32 - 1) {
             if ((uint32_t)lane < llen) c.pref[lane] = pf0;
             if ((uint32_t)lane + 32 < llen) c.pref[lane + 32] = pf1;
@@ -479,7 +555,7 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[C
     }
 }
 
-template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false>
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false, int STORE = 0>
 __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hnsw_search_kernel(const SearchArgs p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
@@ -489,6 +565,8 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
     c.bind(smem, L, s_ints, p.hash_bits);
     float *qs = (float *)(smem + L.off_q);
     GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
+    g.vec16 = p.vec16;
+    g.d16 = p.d16;
 
     const int tid = threadIdx.x;
     const int sub = tid % LPV, grp = tid / LPV;
@@ -501,31 +579,78 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
     for (uint32_t i = tid; i < HS; i += TEAM) c.hash[i] = kEmpty;
     if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; *c.s_next = 0; }
     __syncthreads();
-    float4 q[CPL];
-#pragma unroll
-    for (int cc = 0; cc < CPL; cc++) {
-        const uint32_t idx = sub + cc * LPV;
-        q[cc] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
     WorkCounters w;
-    // ---- searchKnn prologue: distance to the entry point, greedy descent on levels maxlevel..1 ----
     uint32_t cur = p.entry;
-    if (tid == 0) c.ids[0] = cur;
-    __syncthreads();
-    eval_list<TEAM, LPV, CPL, METRIC>(q, g.vec, d4, c.ids, 1, c.dist, grp, sub);
-    __syncthreads();
-    float curdist = c.dist[0];
-    w.D += 1;
-    for (int level = p.maxlevel; level > 0; --level) greedy_level<TEAM, LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
-    __syncthreads();
+    float curdist;
+    {   // ---- searchKnn prologue: distance to the entry point, greedy descent on levels maxlevel..1 (fp32 rows) ----
+        float4 q[CPL];
+#pragma unroll
+        for (int cc = 0; cc < CPL; cc++) {
+            const uint32_t idx = sub + cc * LPV;
+            q[cc] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (tid == 0) c.ids[0] = cur;
+        __syncthreads();
+        eval_list<TEAM, LPV, CPL, METRIC>(q, g.vec, d4, c.ids, 1, c.dist, grp, sub);
+        __syncthreads();
+        curdist = c.dist[0];
+        w.D += 1;
+        for (int level = p.maxlevel; level > 0; --level) greedy_level<TEAM, LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
+        __syncthreads();
+    }
 
     // ---- searchBaseLayerST on level 0 ----
     int cb, size;
-    beam_level<TEAM, LPV, CPL, METRIC, NB>(c, q, g, 0, p.ef, cur, curdist, cb, size, w, p.flags, p.bufcap);
+    if (STORE == 0) {
+        float4 q[CPL];
+#pragma unroll
+        for (int cc = 0; cc < CPL; cc++) {
+            const uint32_t idx = sub + cc * LPV;
+            q[cc] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        beam_level<TEAM, LPV, CPL, METRIC, NB, 0>(c, q, g, 0, p.ef, cur, curdist, cb, size, w, p.flags, p.bufcap);
+    } else {
+        constexpr int C16 = (CPL + 1) / 2;
+        float4 q[C16 * 2];  // chunk idx covers query elements 8*idx .. 8*idx+7
+#pragma unroll
+        for (int cc = 0; cc < C16; cc++) {
+            const uint32_t idx = sub + cc * LPV;
+            q[2 * cc] = 2 * idx < d4 ? ((const float4 *)qs)[2 * idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            q[2 * cc + 1] = 2 * idx + 1 < d4 ? ((const float4 *)qs)[2 * idx + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        beam_level<TEAM, LPV, CPL, METRIC, false, 1>(c, q, g, 0, p.ef, cur, curdist, cb, size, w, nullptr, p.bufcap);
+    }
 
     // ---- epilogue: first k entries are the result, closest first (hnswalg.h:1315-1322) ----
     const uint64_t *res = cb ? c.buf_b : c.buf_a;
+    if (STORE == 1) {
+        // bf16 traversal: re-evaluate the final buffer with the fp32 rows and re-sort it, so distances are the fp32
+        // ones and near-ties at the k-th place are decided exactly (ef * 4d extra bytes per query)
+        uint64_t *other = cb ? c.buf_a : c.buf_b;
+        uint32_t *rid = (uint32_t *)other;
+        float *rd = (float *)(rid + p.bufcap);
+        for (int i = tid; i < size; i += TEAM) rid[i] = (uint32_t)res[i] & kIdMask;
+        __syncthreads();
+        {
+            float4 q[CPL];
+#pragma unroll
+            for (int cc = 0; cc < CPL; cc++) {
+                const uint32_t idx = sub + cc * LPV;
+                q[cc] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            eval_list<TEAM, LPV, CPL, METRIC>(q, g.vec, d4, rid, size, rd, grp, sub);
+        }
+        __syncthreads();
+        uint64_t *srt = const_cast<uint64_t *>(res);  // the traversal keys are no longer needed
+        for (int i = tid; i < size; i += TEAM) {
+            const uint64_t key = make_key(rd[i], rid[i]);
+            int r = 0;
+            for (int j = 0; j < size; j++) r += make_key(rd[j], rid[j]) < key ? 1 : 0;
+            srt[r] = key;
+        }
+        __syncthreads();
+        w.D += size;
+    }
     if (NB) {
         // results are the non-deleted entries only: compact them to the front (same buffer, other half as scratch)
         uint64_t *tmp = cb ? c.buf_a : c.buf_b;

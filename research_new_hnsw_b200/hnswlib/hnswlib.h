@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <limits>
@@ -236,6 +237,9 @@ inline b200hnsw_params make_params(SpaceInterface<float> *s, size_t max_elements
     memset(&p, 0, sizeof(p));
     p.metric = metric;
     p.storage = B200HNSW_F32;
+    // the reference API has no storage knob: B200HNSW_STORAGE=bf16 selects the bf16 traversal + fp32 re-rank variant
+    if (const char *e = getenv("B200HNSW_STORAGE"))
+        if (!strcmp(e, "bf16") || !strcmp(e, "BF16")) p.storage = B200HNSW_BF16;
     p.device = -1;
     p.allow_replace_deleted = allow_replace_deleted ? 1 : 0;
     p.dim = *(size_t *)s->get_dist_func_param();
