@@ -139,6 +139,8 @@ int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
     int rc = h->ix.flush();
     if (rc) return rc;
+    if (nq == 1 && Q && labels_out && dists_out && k)  // one query per call: coalesce concurrent callers into one launch
+        return h->ix.search_coalesced(Q, k, ef, labels_out, dists_out, counts_out, work_out);
     return h->ix.search_host(Q, nq, k, ef, labels_out, dists_out, counts_out, work_out);
     B200_GUARD_END
 }

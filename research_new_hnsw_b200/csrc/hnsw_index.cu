@@ -1,6 +1,9 @@
 // hnsw_index.cu -- HBM image management and search dispatch for HnswIndex.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
+#include <thread>
 
 #include "hnsw_index.cuh"
 
@@ -337,6 +340,68 @@ __global__ void fill_pad_kernel(float *dd, uint32_t *dc, uint32_t *dw, size_t nq
 void fill_pad_rows(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k, cudaStream_t st) {
     const size_t tot = std::max(nq * k, nq * 4);
     fill_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dd, dc, dw, nq, k);
+}
+
+// Micro-batching of concurrent single-query calls: hnsw_service's pool threads each call
+// searchKnn with one query (main.cpp:59-67).  Callers queue their request; the first one becomes the leader, gives
+// the others a few microseconds to arrive, runs ONE batched launch for every queued request with the same (k, ef)
+// and hands the rows back.  A lone caller pays only the short gather window.
+int HnswIndex::search_coalesced(const float *Q, size_t k, size_t ef_, uint64_t *labels, float *dists, uint32_t *counts,
+                                uint32_t *work) {
+    Pending me{Q, k, ef_, labels, dists, counts, work, 0, false, std::string()};
+    std::unique_lock<std::mutex> lk(co_mu);
+    co_queue.push_back(&me);
+    for (;;) {
+        if (me.done) break;
+        if (co_leader) {  // somebody else is running a batch: wait for it (ours may be in it, or in the next one)
+            co_cv.wait(lk);
+            continue;
+        }
+        co_leader = true;
+        lk.unlock();
+        // gather window: concurrent callers are typically microseconds apart
+        const auto t0 = std::chrono::steady_clock::now();
+        while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(co_window_us)) std::this_thread::yield();
+        lk.lock();
+        std::vector<Pending *> batch;
+        for (auto it = co_queue.begin(); it != co_queue.end();) {
+            if ((*it)->k == me.k && (*it)->ef == me.ef && batch.size() < 1024) {
+                batch.push_back(*it);
+                it = co_queue.erase(it);
+            } else {
+                ++it;
+            }
+        }
+        lk.unlock();
+        const size_t nb = batch.size(), d = host.dim;
+        std::vector<float> q(nb * d);
+        std::vector<uint64_t> l(nb * k);
+        std::vector<float> dd(nb * k);
+        std::vector<uint32_t> c(nb), w(nb * 4);
+        for (size_t i = 0; i < nb; i++) memcpy(q.data() + i * d, batch[i]->q, d * 4);
+        const int rc = search_host(q.data(), nb, k, ef_, l.data(), dd.data(), c.data(), w.data());
+        const std::string err = rc ? std::string(b200hnsw_last_error()) : std::string();
+        lk.lock();
+        for (size_t i = 0; i < nb; i++) {
+            Pending *p = batch[i];
+            if (!rc) {
+                memcpy(p->labels, l.data() + i * k, k * 8);
+                memcpy(p->dists, dd.data() + i * k, k * 4);
+                if (p->counts) *p->counts = c[i];
+                if (p->work) memcpy(p->work, w.data() + i * 4, 16);
+            }
+            p->rc = rc;
+            p->err = err;
+            p->done = true;
+        }
+        co_batches++;
+        co_queries += nb;
+        co_leader = false;
+        co_cv.notify_all();
+    }
+    lk.unlock();
+    if (me.rc) set_error(me.err);
+    return me.rc;
 }
 
 int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,

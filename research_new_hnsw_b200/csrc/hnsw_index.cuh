@@ -1,6 +1,9 @@
 // hnsw_index.cuh -- HierarchicalNSW<float> replacement: host mirror + HBM image + kernel dispatch.
 #pragma once
+#include <condition_variable>
+#include <list>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "device_index.cuh"
@@ -43,6 +46,20 @@ struct HnswIndex {
     size_t scratch_q = 0, scratch_k = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // micro-batching of concurrent single-query calls
+    struct Pending {
+        const float *q; size_t k, ef; uint64_t *labels; float *dists; uint32_t *counts; uint32_t *work;
+        int rc; bool done; std::string err;
+    };
+    std::mutex co_mu;
+    std::condition_variable co_cv;
+    std::list<Pending *> co_queue;
+    bool co_leader = false;
+    unsigned co_window_us = 20;
+    uint64_t co_batches = 0, co_queries = 0;
+    int search_coalesced(const float *Q, size_t k, size_t ef_, uint64_t *labels, float *dists, uint32_t *counts,
+                         uint32_t *work);
 
     ~HnswIndex();
     int init_device();

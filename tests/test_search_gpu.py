@@ -204,3 +204,30 @@ def test_bf16_storage_variant(lib, orc, graphs, name):
         exact = (r["labels"] == c["labels"])
         assert np.all(np.abs(r["dists"][exact] - c["dists"][exact]) <= REL_TOL * np.maximum(1.0, np.abs(c["dists"][exact])))
         assert (np.diff(r["dists"], axis=1) >= 0).all()          # closest first
+
+
+def test_concurrent_single_query_callers_are_coalesced(lib, orc, graphs):
+    """hnsw_service's pattern (main.cpp:59-67): many host threads, one searchKnn each.  Results must equal the batched
+    search, whatever the interleaving (requests are micro-batched into shared launches inside the library)."""
+    import threading
+    s = graphs["l2_d128"]
+    idx = lib.HierarchicalNSW(lib.L2Space(s["d"]), s["path"])
+    idx.setEf(64)
+    want = idx.searchKnnBatch(s["Q"], 10, ef=64)
+    got = [None] * len(s["Q"])
+    errs = []
+
+    def worker(t, nt):
+        try:
+            for i in range(t, len(s["Q"]), nt):
+                got[i] = idx.searchKnn(s["Q"][i], 10)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    nt = 12
+    th = [threading.Thread(target=worker, args=(t, nt)) for t in range(nt)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for i in range(len(s["Q"])):
+        assert [l for _, l in got[i]] == want["labels"][i][::-1].tolist()
