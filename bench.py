@@ -343,13 +343,18 @@ def run_b200(a, rank, local_rank, world):
 
     # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + kernel + D2H inside the timed region
     hq = [torch.from_numpy(b).pin_memory() for b in batches]
+    # page-locked result buffers, as a serving host would keep them
+    pl = torch.empty((a.nq, a.k), dtype=torch.int64).pin_memory()
+    pd = torch.empty((a.nq, a.k), dtype=torch.float32).pin_memory()
+    pc = torch.empty((a.nq,), dtype=torch.int32).pin_memory()
+    hout = {"labels": pl.numpy().view(np.uint64), "dists": pd.numpy(), "counts": pc.numpy().view(np.uint32)}
     for s in range(max(3, a.warmup)):
-        idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef)
+        idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef, out=hout)
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
     for s in range(a.steps):
-        r = idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef)
+        r = idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef, out=hout)
         if world > 1:
             merged(torch.from_numpy(r["labels"].view(np.int64)).to(dev), torch.from_numpy(r["dists"]).to(dev), a.nq)
             torch.cuda.synchronize()
@@ -359,7 +364,7 @@ def run_b200(a, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     h2d = a.nq * a.dim * 4
-    d2h = a.nq * a.k * 12 + a.nq * 4 + a.nq * 16
+    d2h = a.nq * a.k * 12 + a.nq * 4
 
     # ---- C5: batched GPU graph build of the same points (wall clock incl. H2D; not part of the timed search region)
     build_info = None

@@ -236,14 +236,22 @@ class HierarchicalNSW:
     def searchKnnCloserFirst(self, query, k):  # hnswlib.h:205-225
         return self.searchKnn(query, k)[::-1]
 
-    def searchKnnBatch(self, Q, k, ef=0, work=False):
-        """Batched searchKnn through the host-pointer C ABI -> dict(labels[nq,k], dists[nq,k], counts[nq], [work])."""
+    def searchKnnBatch(self, Q, k, ef=0, work=False, out=None):
+        """Batched searchKnn through the host-pointer C ABI -> dict(labels[nq,k], dists[nq,k], counts[nq], [work]).
+        `out` may carry preallocated (e.g. page-locked) `labels`, `dists`, `counts` arrays; with page-locked Q and
+        outputs the library overlaps the copies with the kernels of a large batch."""
         Q = np.ascontiguousarray(Q, np.float32)
         assert Q.ndim == 2 and Q.shape[1] == self.space.dim
         nq = Q.shape[0]
-        labels = np.empty((nq, k), np.uint64)
-        dists = np.empty((nq, k), np.float32)
-        counts = np.zeros(nq, np.uint32)
+        if out is not None:
+            labels, dists, counts = out["labels"], out["dists"], out["counts"]
+            assert labels.shape == (nq, k) and labels.dtype == np.uint64 and labels.flags.c_contiguous
+            assert dists.shape == (nq, k) and dists.dtype == np.float32 and dists.flags.c_contiguous
+            assert counts.shape == (nq,) and counts.dtype == np.uint32
+        else:
+            labels = np.empty((nq, k), np.uint64)
+            dists = np.empty((nq, k), np.float32)
+            counts = np.zeros(nq, np.uint32)
         w = np.zeros((nq, 4), np.uint32) if work else None
         _chk(self._L.b200hnsw_search_batch(self._h, _ptr(Q), nq, k, ef, _ptr(labels), _ptr(dists), _ptr(counts),
                                            _ptr(w)))

@@ -18,7 +18,9 @@ HnswIndex::~HnswIndex() {
     cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev2) cudaEventDestroy(ev2);
     if (stream) cudaStreamDestroy(stream);
+    if (stream2) cudaStreamDestroy(stream2);
 }
 
 int HnswIndex::init_device() {
@@ -415,33 +417,58 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
     B200_CUDA_OK(cudaSetDevice(dev.device));
     int rc = ensure_scratch(nq, k);
     if (rc) return rc;
-    B200_CUDA_OK(cudaMemcpyAsync(dQ, Q, nq * host.dim * 4, cudaMemcpyHostToDevice, stream));
-    B200_CUDA_OK(cudaEventRecord(ev0, stream));
-    rc = launch_search(dQ, nq, k, ef_, dLabels, dDists, dCounts, dWork, stream);
-    if (rc) return rc;
-    B200_CUDA_OK(cudaEventRecord(ev1, stream));
-    B200_CUDA_OK(cudaMemcpyAsync(labels, dLabels, nq * k * 8, cudaMemcpyDeviceToHost, stream));
-    B200_CUDA_OK(cudaMemcpyAsync(dists, dDists, nq * k * 4, cudaMemcpyDeviceToHost, stream));
-    if (counts) B200_CUDA_OK(cudaMemcpyAsync(counts, dCounts, nq * 4, cudaMemcpyDeviceToHost, stream));
-    std::vector<uint32_t> wtmp;
-    uint32_t *w = work;
-    if (!w) {
-        wtmp.resize(nq * 4);
-        w = wtmp.data();
+    // Large batches are cut into chunks that alternate between two streams, so the H2D copy of one chunk and the
+    // D2H copy of the previous one overlap the kernel of the chunk in between (kernels of both streams share the SMs).
+    // Only worth it when every host buffer is page-locked: a copy to or from pageable memory blocks the calling thread.
+    auto pinned = [](const void *p) {
+        if (!p) return true;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool async_ok = nq >= 4096 && pinned(Q) && pinned(labels) && pinned(dists) && pinned(counts) && pinned(work);
+    const size_t chunks = async_ok ? 4 : 1;
+    const size_t per = (nq + chunks - 1) / chunks;
+    if (chunks > 1 && !stream2) {
+        B200_CUDA_OK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+        B200_CUDA_OK(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
     }
-    B200_CUDA_OK(cudaMemcpyAsync(w, dWork, nq * 16, cudaMemcpyDeviceToHost, stream));
+    const size_t d = host.dim;
+    B200_CUDA_OK(cudaEventRecord(ev0, stream));
+    if (chunks > 1) {  // the second stream starts after ev0 so the event pair brackets everything
+        B200_CUDA_OK(cudaStreamWaitEvent(stream2, ev0, 0));
+    }
+    for (size_t c = 0; c < chunks; c++) {
+        const size_t off = c * per;
+        if (off >= nq) break;
+        const size_t n = std::min(per, nq - off);
+        cudaStream_t st = (c & 1) ? stream2 : stream;
+        B200_CUDA_OK(cudaMemcpyAsync(dQ + off * d, Q + off * d, n * d * 4, cudaMemcpyHostToDevice, st));
+        rc = launch_search(dQ + off * d, n, k, ef_, dLabels + off * k, dDists + off * k, dCounts + off, dWork + off * 4, st);
+        if (rc) return rc;
+        B200_CUDA_OK(cudaMemcpyAsync(labels + off * k, dLabels + off * k, n * k * 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(cudaMemcpyAsync(dists + off * k, dDists + off * k, n * k * 4, cudaMemcpyDeviceToHost, st));
+        if (counts) B200_CUDA_OK(cudaMemcpyAsync(counts + off, dCounts + off, n * 4, cudaMemcpyDeviceToHost, st));
+        if (work) B200_CUDA_OK(cudaMemcpyAsync(work + off * 4, dWork + off * 4, n * 16, cudaMemcpyDeviceToHost, st));
+    }
+    if (chunks > 1) {
+        B200_CUDA_OK(cudaEventRecord(ev2, stream2));
+        B200_CUDA_OK(cudaStreamWaitEvent(stream, ev2, 0));
+    }
+    B200_CUDA_OK(cudaEventRecord(ev1, stream));
     B200_CUDA_OK(cudaStreamSynchronize(stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ev0, ev1);
-    stats.last_kernel_ms = ms;
+    stats.last_kernel_ms = ms;  // kernel (+ overlapped copies when chunked)
     stats.queries = nq;
     stats.dist_evals = stats.hops_base = stats.hops_upper = stats.visited_resets = 0;
-    for (size_t i = 0; i < nq; i++) {
-        stats.dist_evals += w[i * 4 + 0];
-        stats.hops_base += w[i * 4 + 1];
-        stats.hops_upper += w[i * 4 + 2];
-        stats.visited_resets += w[i * 4 + 3];
-    }
+    if (work)
+        for (size_t i = 0; i < nq; i++) {
+            stats.dist_evals += work[i * 4 + 0];
+            stats.hops_base += work[i * 4 + 1];
+            stats.hops_upper += work[i * 4 + 2];
+            stats.visited_resets += work[i * 4 + 3];
+        }
     return 0;
 }
 

@@ -44,8 +44,8 @@ struct HnswIndex {
     float *dDists = nullptr;
     uint32_t *dCounts = nullptr, *dWork = nullptr;
     size_t scratch_q = 0, scratch_k = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
 
     // micro-batching of concurrent single-query calls
     struct Pending {
