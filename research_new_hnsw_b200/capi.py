@@ -59,7 +59,8 @@ EXPORTS = [
 
 
 def lib_path():
-    return os.path.join(_HERE, "libb200hnsw.so")
+    # B200HNSW_LIB: alternative build of the same library (kernel-tuning experiments); default is the in-tree build
+    return os.environ.get("B200HNSW_LIB") or os.path.join(_HERE, "libb200hnsw.so")
 
 
 def build_library(verbose=False):
