@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--recall", type=float, default=0.95)
     ap.add_argument("--batches", type=int, default=4, help="distinct query batches cycled through the steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--metric", default="l2", choices=["l2", "ip"],
+                    help="l2 = C2 (SIFT-shaped); ip = C3-style shards (Deep-shaped: unit-norm rows, inner product)")
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
                     help="device copy of the vectors: f32 (default, reference-exact traversal) or bf16 traversal + f32 re-rank")
     return ap.parse_args()
@@ -54,23 +56,41 @@ def recall_at_k(labels, gt):
 
 
 def workload_name(a):
+    if a.metric == "ip":
+        return ("C3-shaped shard: synthetic Deep-shaped (rank-16 + 0.1 noise, unit-norm) %dx%d fp32 inner product, M=%d "
+                "ef_construction=%d, batched searchKnn %d queries k=%d" % (a.n, a.dim, a.M, a.efc, a.nq, a.k))
     return ("C2: synthetic SIFT-shaped (rank-16 + 0.1 noise) %dx%d fp32 L2, M=%d ef_construction=%d, batched searchKnn "
             "%d queries k=%d" % (a.n, a.dim, a.M, a.efc, a.nq, a.k))
 
 
 def shard_data(a, rank):
     from research_new_hnsw_b200.synth import lowrank_data
-    return lowrank_data(a.n, a.dim, seed=1 + 1000 * rank)
+    return lowrank_data(a.n, a.dim, seed=1 + 1000 * rank, normalize=(a.metric == "ip"))
 
 
 def query_batches(a):
     from research_new_hnsw_b200.synth import lowrank_data
-    return [lowrank_data(a.nq, a.dim, seed=2 + 7 * b) for b in range(max(1, a.batches))]
+    return [lowrank_data(a.nq, a.dim, seed=2 + 7 * b, normalize=(a.metric == "ip")) for b in range(max(1, a.batches))]
+
+
+def metric_name(a):
+    if a.metric == "ip":
+        return "QPS @ recall@10>=0.95, %dx%d inner-product shard per GPU" % (a.n, a.dim)
+    return "QPS @ recall@10>=0.95, 1Mx128 L2"
+
+
+def space_of(pkg, a):
+    return pkg.InnerProductSpace(a.dim) if a.metric == "ip" else pkg.L2Space(a.dim)
+
+
+def ref_metric(a):
+    from oracle import bind
+    return bind.IP if a.metric == "ip" else bind.L2
 
 
 def graph_path(a, rank):
     os.makedirs(CACHE, exist_ok=True)
-    return os.path.join(CACHE, "c2_n%d_d%d_M%d_efc%d_r%d.bin" % (a.n, a.dim, a.M, a.efc, rank))
+    return os.path.join(CACHE, "%s_n%d_d%d_M%d_efc%d_r%d.bin" % (a.metric, a.n, a.dim, a.M, a.efc, rank))
 
 
 def build_graph_with_reference(a, rank, X, threads):
@@ -81,7 +101,7 @@ def build_graph_with_reference(a, rank, X, threads):
     if os.path.exists(path) and os.path.getsize(path) > 96 + a.n * (a.dim * 4 + 8 * a.M + 12):
         return path, 0.0
     ref = bind.Ref(bind.best_ref_level())
-    idx = ref.hnsw_new(bind.L2, a.dim, a.n, a.M, a.efc)
+    idx = ref.hnsw_new(ref_metric(a), a.dim, a.n, a.M, a.efc)
     labels = np.arange(a.n, dtype=np.uint64) + np.uint64(rank * a.n)
     sec = idx.add(X, labels, threads=threads)
     tmp = path + ".tmp%d" % os.getpid()
@@ -158,7 +178,7 @@ def cpu_reference_leg(a, path, batches, ef, budget_s, threads):
     from oracle import bind
     level = bind.best_ref_level()
     ref = bind.Ref(level)
-    idx = ref.hnsw_load(bind.L2, a.dim, path)
+    idx = ref.hnsw_load(ref_metric(a), a.dim, path)
     idx.search(batches[0][:2000], a.k, ef, threads=threads)  # warm-up: per-thread VisitedList allocation
     done, sec, i = 0, 0.0, 0
     while sec < budget_s and i < 64:
@@ -195,12 +215,12 @@ def run_reference(a, rank, world):
     batches = query_batches(a)
     path, build_s = build_graph_with_reference(a, 0, X, threads)
     ref = bind.Ref(bind.best_ref_level())
-    bf = ref.bf_new(bind.L2, a.dim, a.n)
+    bf = ref.bf_new(ref_metric(a), a.dim, a.n)
     bf.add(X)
     Qs = batches[0][:1000]
     gt = bf.search(Qs, a.k, threads=threads)["labels"]
     del bf
-    idx = ref.hnsw_load(bind.L2, a.dim, path)
+    idx = ref.hnsw_load(ref_metric(a), a.dim, path)
     ef, rec, table = pick_ef(a, lambda Q, e: idx.search(Q, a.k, e, threads=threads)["labels"], gt, Qs)
     for _ in range(a.warmup):
         idx.search(batches[0][:2000], a.k, ef, threads=threads)
@@ -210,7 +230,7 @@ def run_reference(a, rank, world):
     for s in range(a.steps):
         sec += idx.search(batches[s % len(batches)][:sample], a.k, ef, threads=threads)["seconds"]
     qps = a.steps * sample / sec
-    line = {"impl": "reference", "metric": "QPS @ recall@10>=0.95, 1Mx128 L2", "value": qps, "unit": "queries/s",
+    line = {"impl": "reference", "metric": metric_name(a), "value": qps, "unit": "queries/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
@@ -242,7 +262,7 @@ def run_b200(a, rank, local_rank, world):
         # the graph both arms search: built by the reference on the host cores, loaded from its saveIndex file
         path, build_s = build_graph_with_reference(a, rank, X, threads)
         t0 = time.time()
-        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), path, device=local_rank, storage=1 if a.storage == "bf16" else 0)
+        idx = pkg.HierarchicalNSW(space_of(pkg, a), path, device=local_rank, storage=1 if a.storage == "bf16" else 0)
         load_s = time.time() - t0
         graph_note = "reference-built saveIndex file%s, loaded in %.1f s" % (
             "" if build_s == 0 else " (%.1f s, %.0f points/s on %d threads)" % (build_s, a.n / build_s, threads), load_s)
@@ -250,7 +270,7 @@ def run_b200(a, rank, local_rank, world):
         # one sub-index per GPU, built on that GPU (batched addPoint, csrc/build.cu)
         path = None
         t0 = time.time()
-        idx = pkg.HierarchicalNSW(pkg.L2Space(a.dim), a.n, a.M, a.efc, device=local_rank,
+        idx = pkg.HierarchicalNSW(space_of(pkg, a), a.n, a.M, a.efc, device=local_rank,
                                   storage=1 if a.storage == "bf16" else 0)
         idx.addPoints(X, shard_labels)
         idx.flush()
@@ -259,7 +279,7 @@ def run_b200(a, rank, local_rank, world):
 
     # exact ground truth for the first 1000 queries from the exact-scan kernel (global over all shards when N > 1)
     Qs = batches[0][:1000]
-    bf = pkg.BruteforceSearch(pkg.L2Space(a.dim), a.n, device=local_rank)
+    bf = pkg.BruteforceSearch(space_of(pkg, a), a.n, device=local_rank)
     bf.addPoints(X, shard_labels)
     g = bf.searchKnnBatch(Qs, a.k)
     del bf
@@ -371,7 +391,7 @@ def run_b200(a, rank, local_rank, world):
     if rank == 0 and world == 1 and not os.environ.get("B200HNSW_BENCH_SKIP_BUILD"):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        gi = pkg.HierarchicalNSW(pkg.L2Space(a.dim), a.n, a.M, a.efc, device=local_rank)
+        gi = pkg.HierarchicalNSW(space_of(pkg, a), a.n, a.M, a.efc, device=local_rank)
         gi.addPoints(X, shard_labels)
         gi.flush()
         gsec = time.perf_counter() - t0
@@ -406,7 +426,7 @@ def run_b200(a, rank, local_rank, world):
                 cpu_leg = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference",
                            "sample": "unavailable: %s" % e}
         line = {
-            "metric": "QPS @ recall@10>=0.95, 1Mx128 L2", "value": world * a.nq * a.steps / (ms_total * 1e-3),
+            "metric": metric_name(a), "value": world * a.nq * a.steps / (ms_total * 1e-3),
             "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.storage == "f32" else "f32 accumulate over bf16 rows, f32 re-rank", "data": "synthetic",
@@ -425,7 +445,7 @@ def run_b200(a, rank, local_rank, world):
                     "api": "b200hnsw_search_batch (host pointers, pinned)"},
             "gpu_launches": a.steps * (1 if world == 1 else 2),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "hnsw_search_kernel<8,4,L2>", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "kernel": "hnsw_search_kernel<team %d, %s>" % (64 if a.nq >= 2368 else 128, a.metric), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src,
                          "per_query": {"D": bytes_sum[0][1] / a.nq, "H0": bytes_sum[0][2] / a.nq,
                                        "Hup": bytes_sum[0][3] / a.nq}},
