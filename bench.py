@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="points per GPU (shard size)")
+    ap.add_argument("--n", "--points", dest="n", type=int, default=1_000_000, help="points per GPU (shard size)")
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--M", type=int, default=32)
