@@ -372,12 +372,25 @@ def run_b200(a, rank, local_rank, world):
         idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef, out=hout)
     if dist:
         dist.barrier()
+    dq_buf = torch.empty((a.nq, a.dim), dtype=torch.float32, device=dev)
+
+    def e2e_step(s):
+        if world == 1:  # the reference-facing host-pointer C ABI: H2D + kernel + D2H inside the call
+            idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef, out=hout)
+        else:  # sharded public API: pinned H2D -> per-shard search -> all_gather + merge -> D2H of the merged rows
+            dq_buf.copy_(hq[s % len(hq)], non_blocking=True)
+            ol_, od_ = dev_search(dq_buf, a.nq, ef)
+            pl.copy_(ol_, non_blocking=True)
+            pd.copy_(od_, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for s in range(3):
+        e2e_step(s)
+    if dist:
+        dist.barrier()
     t0 = time.perf_counter()
     for s in range(a.steps):
-        r = idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef, out=hout)
-        if world > 1:
-            merged(torch.from_numpy(r["labels"].view(np.int64)).to(dev), torch.from_numpy(r["dists"]).to(dev), a.nq)
-            torch.cuda.synchronize()
+        e2e_step(s)
     e2e_s = time.perf_counter() - t0
     if dist:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -442,7 +455,8 @@ def run_b200(a, rank, local_rank, world):
             "clocks": clocks,
             "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
-                    "api": "b200hnsw_search_batch (host pointers, pinned)"},
+                    "api": "b200hnsw_search_batch (host pointers, pinned)" if world == 1 else
+                           "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},
             "gpu_launches": a.steps * (1 if world == 1 else 2),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "hnsw_search_kernel<team %d, %s>" % (64 if a.nq >= 2368 else 128, a.metric), "kernel_ms": kernel_ms,
