@@ -119,6 +119,14 @@ int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k
 int b200hnsw_search_batch_device(b200hnsw_index *h, const float *dQ, size_t nq, size_t k, size_t ef,
                                  uint64_t *d_labels_out, float *d_dists_out, uint32_t *d_counts_out,
                                  uint32_t *d_work_out, void *cuda_stream);
+/* searchKnn with a BaseFilterFunctor (hnswlib.h:128-132, hnswalg.h:1270,1306-1313): the functor is a host callback, so
+ * the caller evaluates it once per stored label and passes the verdicts -- allowed[i] != 0 for INTERNAL id i,
+ * cur_element_count bytes (NULL = no filter).  A node that is not allowed is traversed but never returned, exactly like
+ * a deleted one (hnswalg.h:406-407). */
+int b200hnsw_search_batch_filtered(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef,
+                                   const uint8_t *allowed, uint64_t *labels_out, float *dists_out, uint32_t *counts_out);
+/* getExternalLabel for every internal id 0 .. cur_element_count-1 (bulk form of hnswalg.h:186-190). */
+int b200hnsw_get_labels(b200hnsw_index *h, uint64_t *labels_out, size_t capacity);
 /* Public fields / accessors the consumers touch. */
 int b200hnsw_get_info(b200hnsw_index *h, b200hnsw_info *out);
 /* element_levels_ (hnswalg.h:52): pointer to cur_element_count ints, valid until the next mutating call. */

@@ -49,7 +49,7 @@ class _Stats(C.Structure):
 EXPORTS = [
     "b200hnsw_last_error", "b200hnsw_abi_version", "b200hnsw_device_count", "b200hnsw_create", "b200hnsw_load",
     "b200hnsw_save", "b200hnsw_destroy", "b200hnsw_set_ef", "b200hnsw_add_batch", "b200hnsw_flush",
-    "b200hnsw_search_batch", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
+    "b200hnsw_search_batch", "b200hnsw_search_batch_filtered", "b200hnsw_get_labels", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
     "b200hnsw_get_linklist", "b200hnsw_get_label", "b200hnsw_get_data", "b200hnsw_get_data_by_label",
     "b200hnsw_mark_delete", "b200hnsw_unmark_delete", "b200hnsw_resize", "b200hnsw_index_file_size",
     "b200hnsw_get_stats", "b200hnsw_merge_topk_device", "b200bf_create", "b200bf_load", "b200bf_save",
@@ -95,6 +95,8 @@ def load_library():
     L.b200hnsw_flush.argtypes = [vp]
     L.b200hnsw_search_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp]
     L.b200hnsw_search_batch_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp, vp]
+    L.b200hnsw_search_batch_filtered.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp]
+    L.b200hnsw_get_labels.argtypes = [vp, vp, sz]
     L.b200hnsw_get_info.argtypes = [vp, C.POINTER(_Info)]
     L.b200hnsw_get_levels.argtypes = [vp, C.POINTER(C.POINTER(C.c_int32))]
     L.b200hnsw_get_linklist.argtypes = [vp, u32, i32, C.POINTER(C.POINTER(C.c_uint32))]
@@ -260,6 +262,21 @@ class HierarchicalNSW:
         if work:
             out.update(D=w[:, 0].copy(), H0=w[:, 1].copy(), Hup=w[:, 2].copy(), resets=w[:, 3].copy())
         return out
+
+    def searchKnnFiltered(self, Q, k, is_id_allowed, ef=0):
+        """searchKnn(query, k, isIdAllowed) batched: `is_id_allowed(label) -> bool` plays BaseFilterFunctor
+        (hnswlib.h:128-132); it is evaluated once per stored label on the host."""
+        Q = np.ascontiguousarray(Q, np.float32)
+        nq, n = Q.shape[0], self.cur_element_count
+        lab = np.empty(max(n, 1), np.uint64)
+        _chk(self._L.b200hnsw_get_labels(self._h, _ptr(lab), lab.size))
+        allowed = np.fromiter((1 if is_id_allowed(int(l)) else 0 for l in lab[:n]), np.uint8, n)
+        labels = np.empty((nq, k), np.uint64)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        _chk(self._L.b200hnsw_search_batch_filtered(self._h, _ptr(Q), nq, k, ef, _ptr(allowed), _ptr(labels),
+                                                    _ptr(dists), _ptr(counts)))
+        return dict(labels=labels, dists=dists, counts=counts)
 
     def searchKnnDevice(self, dQ, nq, k, ef, d_labels, d_dists, d_counts=0, d_work=0, stream=0):
         """Device-pointer search (raw addresses, e.g. torch ``tensor.data_ptr()``), asynchronous on ``stream``."""

@@ -145,6 +145,24 @@ int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k
     B200_GUARD_END
 }
 
+int b200hnsw_search_batch_filtered(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef,
+                                   const uint8_t *allowed, uint64_t *labels_out, float *dists_out, uint32_t *counts_out) {
+    B200_GUARD_BEGIN
+    if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    int rc = h->ix.flush();
+    if (rc) return rc;
+    return h->ix.search_host(Q, nq, k, ef, labels_out, dists_out, counts_out, nullptr, allowed);
+    B200_GUARD_END
+}
+
+int b200hnsw_get_labels(b200hnsw_index *h, uint64_t *labels_out, size_t capacity) {
+    if (!h || !labels_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    const b200::HostImage &m = h->ix.host;
+    if (capacity < m.cur) { set_error("labels_out is smaller than cur_element_count"); return B200HNSW_E_ARG; }
+    for (size_t i = 0; i < m.cur; i++) labels_out[i] = m.label(i);
+    return 0;
+}
+
 int b200hnsw_search_batch_device(b200hnsw_index *h, const float *dQ, size_t nq, size_t k, size_t ef,
                                  uint64_t *d_labels_out, float *d_dists_out, uint32_t *d_counts_out,
                                  uint32_t *d_work_out, void *cuda_stream) {

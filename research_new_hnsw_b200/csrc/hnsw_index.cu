@@ -170,14 +170,16 @@ int HnswIndex::upload_all() {
 }
 
 // delete marks (byte 2 of the level-0 record header, hnswalg.h:934-937) -> device byte array
-int HnswIndex::upload_flags() {
-    if (!flags_dirty && dev.flags) return 0;
+// `allowed` (nullable, one byte per internal id) is a BaseFilterFunctor evaluated by the caller: a node that is not
+// allowed is kept out of top_candidates exactly like a deleted one (hnswalg.h:406-407), so both share the flag byte.
+int HnswIndex::upload_flags(const uint8_t *allowed) {
+    if (!flags_dirty && dev.flags && !allowed) return 0;
     B200_CUDA_OK(cudaSetDevice(dev.device));
     if (!dev.flags) B200_CUDA_OK(cudaMalloc(&dev.flags, std::max<size_t>(dev.cap, 1)));
     std::vector<uint8_t> f(host.cur);
-    for (size_t i = 0; i < host.cur; i++) f[i] = host.deleted(i) ? 1 : 0;
+    for (size_t i = 0; i < host.cur; i++) f[i] = (host.deleted(i) || (allowed && !allowed[i])) ? 1 : 0;
     if (host.cur) B200_CUDA_OK(cudaMemcpy(dev.flags, f.data(), host.cur, cudaMemcpyHostToDevice));
-    flags_dirty = false;
+    flags_dirty = allowed != nullptr;  // a per-call filter must not outlive its call
     return 0;
 }
 
@@ -274,20 +276,20 @@ int pick_team(size_t nq) {
 }
 
 int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd,
-                             uint32_t *dc, uint32_t *dw, cudaStream_t st) {
+                             uint32_t *dc, uint32_t *dw, cudaStream_t st, const uint8_t *allowed) {
     if (nq == 0) return 0;
     if (k == 0 || !dQ_ || !dl || !dd) {
         set_error("search: null pointer or k == 0");
         return B200HNSW_E_ARG;
     }
     B200_CUDA_OK(cudaSetDevice(dev.device));
-    const bool nonbare = host.num_deleted != 0;  // hnswalg.h:1306: bare_bone_search = !num_deleted_ && !isIdAllowed
+    const bool nonbare = host.num_deleted != 0 || allowed;  // hnswalg.h:1306: bare_bone = !num_deleted_ && !isIdAllowed
     if (nonbare) {
         if (linked >= (1u << 30)) {
             set_error("search with deleted elements supports at most 2^30 elements");
             return B200HNSW_E_UNSUPPORTED;
         }
-        int rc = upload_flags();
+        int rc = upload_flags(allowed);
         if (rc) return rc;
     }
     if (linked == 0) {  // hnswalg.h:1273: empty index -> empty result
@@ -407,7 +409,7 @@ int HnswIndex::search_coalesced(const float *Q, size_t k, size_t ef_, uint64_t *
 }
 
 int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
-                           uint32_t *counts, uint32_t *work) {
+                           uint32_t *counts, uint32_t *work, const uint8_t *allowed) {
     if (nq == 0) return 0;
     if (!Q || !labels || !dists || k == 0) {
         set_error("search: null pointer or k == 0");
@@ -426,7 +428,7 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return at.type == cudaMemoryTypeHost;
     };
-    const bool async_ok = nq >= 4096 && pinned(Q) && pinned(labels) && pinned(dists) && pinned(counts) && pinned(work);
+    const bool async_ok = !allowed && nq >= 4096 && pinned(Q) && pinned(labels) && pinned(dists) && pinned(counts) && pinned(work);
     const size_t chunks = async_ok ? 4 : 1;
     const size_t per = (nq + chunks - 1) / chunks;
     if (chunks > 1 && !stream2) {
@@ -444,7 +446,8 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
         const size_t n = std::min(per, nq - off);
         cudaStream_t st = (c & 1) ? stream2 : stream;
         B200_CUDA_OK(cudaMemcpyAsync(dQ + off * d, Q + off * d, n * d * 4, cudaMemcpyHostToDevice, st));
-        rc = launch_search(dQ + off * d, n, k, ef_, dLabels + off * k, dDists + off * k, dCounts + off, dWork + off * 4, st);
+        rc = launch_search(dQ + off * d, n, k, ef_, dLabels + off * k, dDists + off * k, dCounts + off, dWork + off * 4, st,
+                           allowed);
         if (rc) return rc;
         B200_CUDA_OK(cudaMemcpyAsync(labels + off * k, dLabels + off * k, n * k * 8, cudaMemcpyDeviceToHost, st));
         B200_CUDA_OK(cudaMemcpyAsync(dists + off * k, dDists + off * k, n * k * 4, cudaMemcpyDeviceToHost, st));

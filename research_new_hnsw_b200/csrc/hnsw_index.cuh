@@ -67,12 +67,12 @@ struct HnswIndex {
     int upload_all();                       // host mirror -> HBM (after load)
     int upload_upper();                     // rebuild up_base / links_up from the host mirror
     int ensure_scratch(size_t nq, size_t k);
-    int upload_flags();
+    int upload_flags(const uint8_t *allowed = nullptr);
     int sync_bf16(size_t first, size_t count);
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
-                      uint32_t *dw, cudaStream_t st);
+                      uint32_t *dw, cudaStream_t st, const uint8_t *allowed = nullptr);
     int search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
-                    uint32_t *counts, uint32_t *work);
+                    uint32_t *counts, uint32_t *work, const uint8_t *allowed = nullptr);
     // build.cu: addPoint staging and the batched GPU graph build
     int add_batch(const float *X, const uint64_t *labels, size_t n);
     int flush();

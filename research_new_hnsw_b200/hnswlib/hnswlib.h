@@ -511,13 +511,24 @@ class HierarchicalNSW : public AlgorithmInterface<dist_t> {
 
     std::priority_queue<std::pair<dist_t, labeltype>> searchKnn(const void *query_data, size_t k,
                                                                 BaseFilterFunctor *isIdAllowed = nullptr) const {
-        if (isIdAllowed)
-            throw std::runtime_error("BaseFilterFunctor host callbacks are not supported by the GPU engine");
         std::priority_queue<std::pair<dist_t, labeltype>> result;
         if (cur_element_count == 0 || k == 0) return result;
         std::vector<uint64_t> labels(k);
         std::vector<float> dists(k);
         uint32_t cnt = 0;
+        if (isIdAllowed) {
+            // the functor is a host callback: evaluate it once per stored label, the kernel treats "not allowed" like a
+            // delete mark (hnswalg.h:406-407)
+            const size_t n = cur_element_count;
+            std::vector<uint64_t> all(n);
+            b200detail::check(b200hnsw_get_labels(h_, all.data(), n));
+            std::vector<uint8_t> allowed(n);
+            for (size_t i = 0; i < n; i++) allowed[i] = (*isIdAllowed)((labeltype)all[i]) ? 1 : 0;
+            b200detail::check(b200hnsw_search_batch_filtered(h_, (const float *)query_data, 1, k, 0, allowed.data(),
+                                                             labels.data(), dists.data(), &cnt));
+            for (uint32_t j = 0; j < cnt; j++) result.emplace(dists[j], (labeltype)labels[j]);
+            return result;
+        }
         uint32_t work[4] = {0, 0, 0, 0};
         b200detail::check(b200hnsw_search_batch(h_, (const float *)query_data, 1, k, 0, labels.data(), dists.data(), &cnt, work));
         metric_distance_computations += work[0];

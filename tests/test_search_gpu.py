@@ -231,3 +231,21 @@ def test_concurrent_single_query_callers_are_coalesced(lib, orc, graphs):
     assert not errs, errs
     for i in range(len(s["Q"])):
         assert [l for _, l in got[i]] == want["labels"][i][::-1].tolist()
+
+
+def test_filter_functor_is_a_per_call_delete_mask(lib, orc, graphs):
+    """searchKnn(query, k, isIdAllowed) (hnswalg.h:1270,1306-1313): a node the functor rejects is traversed but never
+    returned -- the same branch as a delete mark (:406-407), which is how the oracle states the expectation."""
+    s = graphs["l2_d128"]
+    idx = lib.HierarchicalNSW(lib.L2Space(s["d"]), s["path"])
+    cpu = orc.hnsw_load(s["metric"], s["d"], s["path"])
+    allow = lambda label: label % 3 != 0
+    for l in range(0, s["n"], 3):
+        cpu.mark_delete(l)
+    r = idx.searchKnnFiltered(s["Q"], 10, allow, ef=64)
+    c = cpu.search(s["Q"], 10, 64)
+    assert (r["labels"] % 3 != 0).all()
+    _check(r, c, "filter")
+    # the filter does not stick to the index: the next plain search is bare-bone again
+    bare = orc.hnsw_load(s["metric"], s["d"], s["path"]).search(s["Q"], 10, 64)
+    _check(idx.searchKnnBatch(s["Q"], 10, ef=64), bare, "after filter")
