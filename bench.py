@@ -24,7 +24,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-EF_SWEEP = [12, 16, 20, 24, 28, 32, 40, 48, 64, 96, 128, 192, 256]
+EF_SWEEP = [10, 12, 14, 16, 18, 20, 22, 24, 26, 28, 30, 32, 36, 40, 48, 56, 64, 96, 128, 192, 256]
 CACHE = os.environ.get("B200HNSW_CACHE", "/tmp/b200hnsw_cache")
 
 
