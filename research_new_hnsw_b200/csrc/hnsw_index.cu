@@ -429,7 +429,9 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
         return at.type == cudaMemoryTypeHost;
     };
     const bool async_ok = !allowed && nq >= 4096 && pinned(Q) && pinned(labels) && pinned(dists) && pinned(counts) && pinned(work);
-    const size_t chunks = async_ok ? 4 : 1;
+    size_t chunks = async_ok ? 3 : 1;  // measured: 3 chunks beat 2 and 4+ (smaller kernels lose more to their tails)
+    if (async_ok)
+        if (const char *e = getenv("B200HNSW_CHUNKS")) chunks = (size_t)std::min(16, std::max(1, atoi(e)));
     const size_t per = (nq + chunks - 1) / chunks;
     if (chunks > 1 && !stream2) {
         B200_CUDA_OK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
