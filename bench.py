@@ -210,6 +210,11 @@ def run_reference(a, rank, world):
     if rank != 0:
         return
     from oracle import bind
+    if not bind.ref_available("sse"):
+        # the compiled reference (oracle/_ref, built from /root/reference in the build container) did not travel
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libhnswref_sse.so is missing on this box"}),
+              flush=True)
+        return
     threads = os.cpu_count() or 1
     X = shard_data(a, 0)
     batches = query_batches(a)

@@ -37,7 +37,7 @@ thread_local std::string t_err;
 struct CountCtx {
     hnswlib::DISTFUNC<float> fn;
     void *param;
-    size_t dim;  // getDataByLabel reads *(size_t*)dist_func_param_ -> keep dim first-compatible
+    size_t dim;
 };
 
 float counting_dist(const void *a, const void *b, const void *ctxv) {
