@@ -486,7 +486,14 @@ int HnswIndex::flush() {
     a.aff_node = bld.aff_node; a.aff_level = bld.aff_level; a.aff_count = bld.aff_count; a.work = bld.work;
     a.cap = (uint32_t)dev.cap; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)m.maxM; a.maxM0 = (uint32_t)m.maxM0;
     a.M = (uint32_t)m.M; a.efc = (uint32_t)m.efc;
-    a.hash_bits = pick_hash_bits(m.efc, list_cap);
+    // construction searches evaluate ~40 * efc nodes; a table of ~32 * efc slots is rebuilt about once in four searches
+    // and lets twice as many CTAs share an SM as the no-rebuild size (measured: -30 % build time, same graph)
+    {
+        size_t want = std::min<size_t>(8192, 32 * m.efc + 1024);
+        want = std::max(want, 2 * (m.efc + list_cap));
+        a.hash_bits = 10;
+        while ((1ull << a.hash_bits) < want) a.hash_bits++;
+    }
     const SearchSmem SL(a.efc, (uint32_t)list_cap, a.d4, a.hash_bits);
     const LinkSmem LL((uint32_t)list_cap + kCapIn);
     if (SL.total > 226 * 1024) {

@@ -214,8 +214,10 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
     }
     size_t want = 64 * ef + 1024;
     if (want > 16384) want = 16384;
-    if (team == 64) want /= 2;
-    if (team == 32) want /= 4;
+    // Throughput teams (64 / 32 threads): resident queries per SM matter more than avoiding rebuilds.  Measured on the
+    // 1M x 128 graph, 10 k queries (ms per batch, default-size table vs this policy): ef=64 3.31 -> 2.79, ef=128
+    // 8.82 -> 5.18, ef=256 20.3 -> 10.0, with 7-20 % more evaluations from the rebuilds.
+    if (team <= 64) want = ef <= 64 ? 2048 : 1024;
     if (want < need) want = need;
     uint32_t bits = 10;
     while ((1ull << bits) < want) bits++;
