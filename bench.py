@@ -227,6 +227,11 @@ def run_reference(a, rank, world):
     del bf
     idx = ref.hnsw_load(ref_metric(a), a.dim, path)
     ef, rec, table = pick_ef(a, lambda Q, e: idx.search(Q, a.k, e, threads=threads)["labels"], gt, Qs)
+    ef_table = []
+    for e in (16, 32, 48, 64, 96, 128, 192, 256):
+        r_e = idx.search(batches[0][:2000], a.k, e, threads=threads)
+        ef_table.append({"ef": e, "recall_at_10": round(recall_at_k(r_e["labels"][:1000], gt), 4),
+                         "qps": 2000 / r_e["seconds"]})
     for _ in range(a.warmup):
         idx.search(batches[0][:2000], a.k, ef, threads=threads)
     sec = 0.0
@@ -239,6 +244,7 @@ def run_reference(a, rank, world):
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
+                       "ef_table": ef_table,
                        "graph": "built by the reference (addPoint, %d threads)%s" %
                                 (threads, "" if build_s == 0 else " in %.1f s = %.0f points/s" % (build_s, a.n / build_s)),
                        "step": "%d queries of the batch" % sample},
@@ -366,6 +372,21 @@ def run_b200(a, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
 
+    # ---- C2's ef sweep (32..256): device-resident QPS and recall per ef, outside the headline timed region
+    ef_table = []
+    if world == 1:
+        for e in (16, 32, 48, 64, 96, 128, 192, 256):
+            rec_e = recall_at_k(sweep_fn(Qs, e), gt)
+            dev_search(dbatches[0], a.nq, e)
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for s in range(3):
+                dev_search(dbatches[s % len(dbatches)], a.nq, e)
+            t1e.record()
+            torch.cuda.synchronize()
+            ef_table.append({"ef": e, "recall_at_10": round(rec_e, 4), "qps": 3 * a.nq / (t0e.elapsed_time(t1e) * 1e-3)})
+
     # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + kernel + D2H inside the timed region
     hq = [torch.from_numpy(b).pin_memory() for b in batches]
     # page-locked result buffers, as a serving host would keep them
@@ -449,7 +470,7 @@ def run_b200(a, rank, local_rank, world):
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.storage == "f32" else "f32 accumulate over bf16 rows, f32 re-rank", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
-                       "storage": a.storage,
+                       "storage": a.storage, "ef_table": ef_table,
                        "parallelism": "1 GPU" if world == 1 else
                        "shard%d: one %d-point sub-index per GPU, queries replicated, NCCL all_gather + GPU merge; value "
                        "counts shard-level searches (merged queries/s = value/%d)" % (world, a.n, world),
