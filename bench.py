@@ -309,7 +309,15 @@ def run_b200(a, rank, local_rank, world):
     gt_l, _ = merged(gt_l, gt_d, len(Qs))
     gt = gt_l.cpu().numpy().view(np.uint64)
 
+    from research_new_hnsw_b200.sharded import PackedShardExchange
+    packed = PackedShardExchange(a.nq, a.k, dev) if world > 1 else None
+
     def dev_search(dQ, nq, ef, work=None):
+        if packed is not None and nq == a.nq:
+            # full batches at N > 1: results go straight into this rank's block, one all_gather, one merge launch
+            pl_, pd_ = packed.local_ptrs()
+            idx.searchKnnDevice(dQ.data_ptr(), nq, a.k, ef, pl_, pd_, 0, work.data_ptr() if work is not None else 0, stream)
+            return packed.exchange_and_merge(stream)
         ol = torch.empty((nq, a.k), dtype=torch.int64, device=dev)
         od = torch.empty((nq, a.k), dtype=torch.float32, device=dev)
         idx.searchKnnDevice(dQ.data_ptr(), nq, a.k, ef, ol.data_ptr(), od.data_ptr(), 0,
@@ -337,8 +345,17 @@ def run_b200(a, rank, local_rank, world):
         dev_search(dQ, a.nq, ef, w)
         torch.cuda.synchronize()
         works.append(w.cpu().numpy().astype(np.int64))
+    from research_new_hnsw_b200.sharded import PipelinedShardSearch
+    pipe = None
+    if world > 1 and not os.environ.get("B200HNSW_BENCH_NO_PIPELINE"):
+        pipe = PipelinedShardSearch(idx, a.nq, a.k, dev, depth=int(os.environ.get("B200HNSW_PIPE_DEPTH", "2")))
     for s in range(a.warmup):
-        dev_search(dbatches[s % len(dbatches)], a.nq, ef)
+        if pipe is not None:
+            pipe.submit(dbatches[s % len(dbatches)].data_ptr(), ef)
+        else:
+            dev_search(dbatches[s % len(dbatches)], a.nq, ef)
+    if pipe is not None:
+        pipe.drain()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -347,8 +364,18 @@ def run_b200(a, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    for s in range(a.steps):
-        dev_search(dbatches[s % len(dbatches)], a.nq, ef)
+    submit_ms = None
+    if pipe is not None:
+        # N > 1: batch i's all_gather + merge overlaps batch i+1's search kernel (side stream, event-ordered);
+        # the timed region ends only after the last exchange has finished.
+        t_submit = time.perf_counter()
+        for s in range(a.steps):
+            pipe.submit(dbatches[s % len(dbatches)].data_ptr(), ef)
+        submit_ms = 1e3 * (time.perf_counter() - t_submit) / a.steps
+        pipe.drain()
+    else:
+        for s in range(a.steps):
+            dev_search(dbatches[s % len(dbatches)], a.nq, ef)
     ev1.record()
     torch.cuda.synchronize()
     if dist:
@@ -367,10 +394,17 @@ def run_b200(a, rank, local_rank, world):
     k1.record()
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / a.steps
+    rank_diag = None
     if dist:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+        # per-rank diagnostics: search-kernel ms and host submit ms per step (explains step time vs kernel time)
+        mine = torch.tensor([kernel_ms, submit_ms or 0.0], device=dev, dtype=torch.float64)
+        allr = torch.empty((world, 2), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        rank_diag = {"kernel_ms": [round(x, 4) for x in allr[:, 0].tolist()],
+                     "host_submit_ms": [round(x, 4) for x in allr[:, 1].tolist()]}
 
     # ---- C2's ef sweep (32..256): device-resident QPS and recall per ef, outside the headline timed region
     ef_table = []
@@ -472,18 +506,19 @@ def run_b200(a, rank, local_rank, world):
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
                        "storage": a.storage, "ef_table": ef_table,
                        "parallelism": "1 GPU" if world == 1 else
-                       "shard%d: one %d-point sub-index per GPU, queries replicated, NCCL all_gather + GPU merge; value "
-                       "counts shard-level searches (merged queries/s = value/%d)" % (world, a.n, world),
+                       "shard%d: one %d-point sub-index per GPU, queries replicated, ONE packed NCCL all_gather + GPU merge "
+                       "per batch%s; value counts shard-level searches (merged queries/s = value/%d)"
+                       % (world, a.n, ", exchange of batch i overlapped with the search of batch i+1" if pipe else "", world),
                        "l2_policy": "inputs larger than L2 (index %.0f MB vs 126 MB L2); %d distinct query batches cycled"
                                     % ((a.n * (a.dim * 4 + 8 * a.M)) / 1e6, len(batches)),
                        "graph": graph_note, "build": build_info,
                        "visited_table_rebuilds_per_batch": resets / len(works)},
-            "clocks": clocks,
+            "clocks": clocks, "per_rank": rank_diag,
             "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
                     "api": "b200hnsw_search_batch (host pointers, pinned)" if world == 1 else
                            "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},
-            "gpu_launches": a.steps * (1 if world == 1 else 2),
+            "gpu_launches": a.steps * (1 if world == 1 else 2),  # search kernel (+ merge kernel at N > 1)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "hnsw_search_kernel<team %d, %s>" % (64 if a.nq >= 2368 else 128, a.metric), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src,

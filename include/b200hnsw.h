@@ -153,6 +153,12 @@ int b200hnsw_get_stats(b200hnsw_index *h, b200hnsw_stats *out);
 int b200hnsw_merge_topk_device(const uint64_t *d_labels_in, const float *d_dists_in, size_t shards, size_t nq,
                                size_t k, uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream);
 
+/* Same merge for blocks packed per shard as [nq*k labels (u64) | nq*k dists (f32) | padding] of block_bytes each
+ * (block_bytes a multiple of 8): a shard writes its search results straight into its block and ONE all_gather moves
+ * both arrays. */
+int b200hnsw_merge_topk_packed_device(const void *d_blocks, size_t block_bytes, size_t shards, size_t nq, size_t k,
+                                      uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream);
+
 /* ---- BruteforceSearch<float> (bruteforce.h) -------------------------------------------------------------- */
 /* BruteforceSearch(space, maxElements), bruteforce.h:48-59 */
 int b200bf_create(const b200hnsw_params *params, b200bf_index **out);

@@ -17,9 +17,10 @@ from .capi import (  # noqa: F401
     lib_path,
     load_library,
     merge_topk_device,
+    merge_topk_packed_device,
 )
 
 __all__ = [
     "B200Error", "BruteforceSearch", "HierarchicalNSW", "InnerProductSpace", "L2Space", "build_library",
-    "device_count", "lib_path", "load_library", "merge_topk_device",
+    "device_count", "lib_path", "load_library", "merge_topk_device", "merge_topk_packed_device",
 ]

@@ -52,7 +52,7 @@ EXPORTS = [
     "b200hnsw_search_batch", "b200hnsw_search_batch_filtered", "b200hnsw_get_labels", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
     "b200hnsw_get_linklist", "b200hnsw_get_label", "b200hnsw_get_data", "b200hnsw_get_data_by_label",
     "b200hnsw_mark_delete", "b200hnsw_unmark_delete", "b200hnsw_resize", "b200hnsw_index_file_size",
-    "b200hnsw_get_stats", "b200hnsw_merge_topk_device", "b200bf_create", "b200bf_load", "b200bf_save",
+    "b200hnsw_get_stats", "b200hnsw_merge_topk_device", "b200hnsw_merge_topk_packed_device", "b200bf_create", "b200bf_load", "b200bf_save",
     "b200bf_destroy", "b200bf_add_batch", "b200bf_remove", "b200bf_search_batch", "b200bf_search_batch_device",
     "b200bf_count", "b200bf_get_stats",
 ]
@@ -109,6 +109,7 @@ def load_library():
     L.b200hnsw_index_file_size.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.b200hnsw_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     L.b200hnsw_merge_topk_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+    L.b200hnsw_merge_topk_packed_device.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
     L.b200bf_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
     L.b200bf_load.argtypes = [C.c_char_p, C.POINTER(_Params), C.POINTER(vp)]
     L.b200bf_save.argtypes = [vp, C.c_char_p]
@@ -399,3 +400,9 @@ def merge_topk_device(d_labels_in, d_dists_in, shards, nq, k, d_labels_out, d_di
     """Merge [shards][nq][k] per-shard results (device pointers) into [nq][k]."""
     _chk(load_library().b200hnsw_merge_topk_device(d_labels_in, d_dists_in, shards, nq, k, d_labels_out, d_dists_out,
                                                    stream or None))
+
+
+def merge_topk_packed_device(d_blocks, block_bytes, shards, nq, k, d_labels_out, d_dists_out, stream=0):
+    """Merge per-shard blocks packed as [labels | dists] (one all_gather moves both arrays)."""
+    _chk(load_library().b200hnsw_merge_topk_packed_device(d_blocks, block_bytes, shards, nq, k, d_labels_out,
+                                                          d_dists_out, stream or None))

@@ -439,7 +439,7 @@ int BruteIndex::search_scan(const float *dQ_, size_t nq, size_t k, uint64_t *dl,
     B200_CUDA_OK(cudaGetLastError());
     const unsigned warps = 4;
     merge_topk_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, st>>>(
-        dPartL, dPartD, (uint32_t)slices, (uint32_t)nq, (uint32_t)k, dl, dd);
+        dPartL, dPartD, nq * k, nq * k, (uint32_t)slices, (uint32_t)nq, (uint32_t)k, dl, dd);
     B200_CUDA_OK(cudaGetLastError());
     if (dc) bf_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(dc, (uint32_t)nq, (uint32_t)std::min(k, n));
     stats.kernel_launches += 2;

@@ -294,19 +294,41 @@ int b200hnsw_get_stats(b200hnsw_index *h, b200hnsw_stats *out) {
     return 0;
 }
 
-int b200hnsw_merge_topk_device(const uint64_t *d_labels_in, const float *d_dists_in, size_t shards, size_t nq,
-                               size_t k, uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream) {
-    B200_GUARD_BEGIN
-    if (!d_labels_in || !d_dists_in || !d_labels_out || !d_dists_out || !shards || !k) {
+static int merge_launch(const uint64_t *l, const float *d, size_t ls, size_t ds, size_t shards, size_t nq, size_t k,
+                        uint64_t *ol, float *od, void *cuda_stream) {
+    if (!l || !d || !ol || !od || !shards || !k) {
         set_error("null argument");
         return B200HNSW_E_ARG;
     }
     if (nq == 0) return 0;
-    const unsigned warps = 4;
-    b200::merge_topk_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, (cudaStream_t)cuda_stream>>>(
-        d_labels_in, d_dists_in, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, d_labels_out, d_dists_out);
+    const size_t total = shards * k;
+    unsigned warps = 4;
+    while (warps > 1 && warps * total * 12 > 48 * 1024) warps >>= 1;
+    const unsigned grid = (unsigned)((nq + warps - 1) / warps);
+    if (warps * total * 12 <= 48 * 1024)
+        b200::merge_topk_smem_kernel<<<grid, warps * 32, warps * total * 12, (cudaStream_t)cuda_stream>>>(
+            l, d, ls, ds, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, ol, od);
+    else  // more than 4096 candidates per query: read them from global memory
+        b200::merge_topk_kernel<<<grid, warps * 32, 0, (cudaStream_t)cuda_stream>>>(
+            l, d, ls, ds, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, ol, od);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int b200hnsw_merge_topk_device(const uint64_t *d_labels_in, const float *d_dists_in, size_t shards, size_t nq,
+                               size_t k, uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream) {
+    B200_GUARD_BEGIN
+    return merge_launch(d_labels_in, d_dists_in, nq * k, nq * k, shards, nq, k, d_labels_out, d_dists_out, cuda_stream);
+    B200_GUARD_END
+}
+
+int b200hnsw_merge_topk_packed_device(const void *d_blocks, size_t block_bytes, size_t shards, size_t nq, size_t k,
+                                      uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream) {
+    B200_GUARD_BEGIN
+    if (block_bytes < nq * k * 12 || block_bytes % 8) { set_error("block_bytes must be >= nq*k*12 and a multiple of 8"); return B200HNSW_E_ARG; }
+    const uint64_t *l = (const uint64_t *)d_blocks;
+    const float *d = (const float *)((const char *)d_blocks + nq * k * 8);
+    return merge_launch(l, d, block_bytes / 8, block_bytes / 4, shards, nq, k, d_labels_out, d_dists_out, cuda_stream);
     B200_GUARD_END
 }
 

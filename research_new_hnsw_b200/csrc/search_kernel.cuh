@@ -689,10 +689,12 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
     }
 }
 
-// k-way merge of per-shard results: one warp per query over shards*k candidates.
+// k-way merge of per-shard results: one warp per query over shards*k candidates.  Shard s holds its
+// rows at labels_in + s*lstride / dists_in + s*dstride (elements), so the per-shard blocks may be packed
+// [labels | dists] and exchanged with ONE all_gather.
 static __global__ void merge_topk_kernel(const uint64_t *__restrict__ labels_in, const float *__restrict__ dists_in,
-                                  uint32_t shards, uint32_t nq, uint32_t k, uint64_t *__restrict__ labels_out,
-                                  float *__restrict__ dists_out) {
+                                         size_t lstride, size_t dstride, uint32_t shards, uint32_t nq, uint32_t k,
+                                         uint64_t *__restrict__ labels_out, float *__restrict__ dists_out) {
     const uint32_t qi = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (qi >= nq) return;
@@ -700,14 +702,56 @@ static __global__ void merge_topk_kernel(const uint64_t *__restrict__ labels_in,
     // rank of every candidate among all candidates by (dist, label); O(total^2/32) per warp, total <= 8*100
     for (uint32_t c = lane; c < total; c += 32) {
         const uint32_t s = c / k, j = c % k;
-        const float dc = dists_in[((size_t)s * nq + qi) * k + j];
-        const uint64_t lc = labels_in[((size_t)s * nq + qi) * k + j];
+        const float dc = dists_in[s * dstride + (size_t)qi * k + j];
+        const uint64_t lc = labels_in[s * lstride + (size_t)qi * k + j];
         uint32_t rank = 0;
         for (uint32_t o = 0; o < total; o++) {
             const uint32_t so = o / k, jo = o % k;
-            const float d2 = dists_in[((size_t)so * nq + qi) * k + jo];
-            const uint64_t l2 = labels_in[((size_t)so * nq + qi) * k + jo];
+            const float d2 = dists_in[so * dstride + (size_t)qi * k + jo];
+            const uint64_t l2 = labels_in[so * lstride + (size_t)qi * k + jo];
             rank += (d2 < dc || (d2 == dc && (l2 < lc || (l2 == lc && o < c)))) ? 1u : 0u;
+        }
+        if (rank < k) {
+            labels_out[(size_t)qi * k + rank] = lc;
+            dists_out[(size_t)qi * k + rank] = dc;
+        }
+    }
+}
+
+// Same contract, candidates staged once into shared memory (coalesced per-shard row reads), ranks computed from
+// shared memory with broadcast reads: the global-memory version above is latency-bound (total^2 dependent loads per
+// warp) and, on a high-priority exchange stream, crowds the search kernel out of the SMs.  Dynamic shared memory:
+// warps_per_cta * total * 12 bytes.
+static __global__ void merge_topk_smem_kernel(const uint64_t *__restrict__ labels_in, const float *__restrict__ dists_in,
+                                              size_t lstride, size_t dstride, uint32_t shards, uint32_t nq, uint32_t k,
+                                              uint64_t *__restrict__ labels_out, float *__restrict__ dists_out) {
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    const uint32_t warps = blockDim.x / 32, w = threadIdx.x / 32;
+    const uint32_t qi = blockIdx.x * warps + w;
+    const int lane = threadIdx.x & 31;
+    if (qi >= nq) return;
+    const uint32_t total = shards * k;
+    uint64_t *sl = reinterpret_cast<uint64_t *>(merge_smem) + (size_t)w * total;
+    float *sd = reinterpret_cast<float *>(merge_smem + (size_t)warps * total * 8) + (size_t)w * total;
+    for (uint32_t c = lane; c < total; c += 32) {
+        const uint32_t s = c / k, j = c % k;
+        sl[c] = labels_in[s * lstride + (size_t)qi * k + j];
+        sd[c] = dists_in[s * dstride + (size_t)qi * k + j];
+    }
+    __syncwarp();
+    for (uint32_t c = lane; c < total; c += 32) {
+        const float dc = sd[c];
+        const uint64_t lc = sl[c];
+        uint32_t rank = 0;
+        for (uint32_t o = 0; o < total; o++) {
+            const float d2 = sd[o];
+            // ties on distance are rare: only then look at the label
+            if (d2 < dc) rank++;
+            else if (d2 == dc) {
+                const uint64_t l2 = sl[o];
+                rank += (l2 < lc || (l2 == lc && o < c)) ? 1u : 0u;
+            }
+            if (rank >= k) break;
         }
         if (rank < k) {
             labels_out[(size_t)qi * k + rank] = lc;

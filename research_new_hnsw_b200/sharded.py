@@ -80,3 +80,78 @@ def cuda_merge(stream_getter=None):
         return ol, od
 
     return merge
+
+
+class PackedShardExchange:
+    """Throughput path of the sharded search: every rank owns a block [labels | dists] of its results, the search
+    kernel writes straight into it, ONE all_gather_into_tensor moves all blocks, the merge kernel reads them in place.
+    All buffers are allocated once (no per-step allocations, one collective, one merge launch per step)."""
+
+    def __init__(self, nq, k, device, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nq, self.k = nq, k
+        self.block = (nq * k * 12 + 7) // 8 * 8
+        self.mine = torch.empty(self.block, dtype=torch.uint8, device=device)
+        self.all = torch.empty(self.world * self.block, dtype=torch.uint8, device=device)
+        self.out_l = torch.empty((nq, k), dtype=torch.int64, device=device)
+        self.out_d = torch.empty((nq, k), dtype=torch.float32, device=device)
+
+    def local_ptrs(self):
+        """device addresses the shard's search must write its labels / dists to"""
+        base = self.mine.data_ptr()
+        return base, base + self.nq * self.k * 8
+
+    def exchange_and_merge(self, stream):
+        from . import capi
+        if self.world == 1:
+            src = self.mine
+        else:
+            self.dist.all_gather_into_tensor(self.all, self.mine, group=self.group)
+            src = self.all
+        capi.merge_topk_packed_device(src.data_ptr(), self.block, self.world, self.nq, self.k, self.out_l.data_ptr(),
+                                      self.out_d.data_ptr(), stream)
+        return self.out_l, self.out_d
+
+
+class PipelinedShardSearch:
+    """Back-to-back batches at N > 1: the exchange (all_gather + merge) of batch i runs on a side stream while the
+    search kernel of batch i+1 already runs on the caller's stream, so collective latency and rank skew are hidden
+    behind compute instead of serialising with it.  ``depth`` result blocks are cycled; a block is reused only after
+    its exchange finished (event wait, no host sync)."""
+
+    def __init__(self, index, nq, k, device, depth=2, group=None):
+        import torch
+        self.torch, self.index, self.nq, self.k = torch, index, nq, k
+        self.slots = [PackedShardExchange(nq, k, device, group) for _ in range(depth)]
+        self.done = [None] * depth
+        self.side = torch.cuda.Stream(device=device, priority=-1)
+        self.i = 0
+
+    def submit(self, d_queries, ef, d_work=0):
+        """enqueue one batch; returns (labels, dists, event) -- the tensors are valid once ``event`` completed"""
+        torch = self.torch
+        main = torch.cuda.current_stream()
+        j = self.i % len(self.slots)
+        self.i += 1
+        slot = self.slots[j]
+        if self.done[j] is not None:
+            main.wait_event(self.done[j])
+        pl, pd = slot.local_ptrs()
+        self.index.searchKnnDevice(d_queries, self.nq, self.k, ef, pl, pd, 0, d_work, main.cuda_stream)
+        searched = torch.cuda.Event()
+        searched.record(main)
+        self.side.wait_event(searched)
+        with torch.cuda.stream(self.side):
+            out_l, out_d = slot.exchange_and_merge(self.side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self.done[j] = ev
+        return out_l, out_d, ev
+
+    def drain(self):
+        """make the caller's stream wait for every exchange in flight"""
+        self.torch.cuda.current_stream().wait_stream(self.side)

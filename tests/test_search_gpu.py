@@ -150,6 +150,19 @@ def test_merge_topk_kernel_matches_reference_semantics(lib):
         gl, gd = cuda_merge()(torch.from_numpy(L.view(np.int64)).cuda(), torch.from_numpy(D).cuda(), k)
         torch.cuda.synchronize()
         assert np.array_equal(gl.cpu().numpy().view(np.uint64), el) and np.array_equal(gd.cpu().numpy(), ed)
+        # packed [labels | dists | pad] blocks (the single-all_gather exchange layout), padded by 16 bytes per block
+        block = (nq * k * 12 + 7) // 8 * 8 + 16
+        blob = np.zeros((shards, block), np.uint8)
+        for s_ in range(shards):
+            blob[s_, :nq * k * 8] = L[s_].reshape(-1).view(np.uint8)
+            blob[s_, nq * k * 8:nq * k * 12] = D[s_].reshape(-1).view(np.uint8)
+        db = torch.from_numpy(blob).cuda()
+        ol = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+        od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+        lib.merge_topk_packed_device(db.data_ptr(), block, shards, nq, k, ol.data_ptr(), od.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(ol.cpu().numpy().view(np.uint64), el) and np.array_equal(od.cpu().numpy(), ed)
 
 
 @pytest.mark.parametrize("name,frac", [("l2_d128", 0.05), ("ip_d96", 0.2), ("lowrank_d128", 0.5)])
