@@ -139,7 +139,7 @@ def test_merge_topk_kernel_matches_reference_semantics(lib):
     import torch
     from research_new_hnsw_b200.sharded import cuda_merge, merge_topk_numpy
     rng = np.random.default_rng(5)
-    for shards, nq, k in [(2, 100, 10), (8, 257, 10), (4, 33, 100), (3, 5, 1)]:
+    for shards, nq, k in [(2, 100, 10), (8, 257, 10), (4, 33, 100), (3, 5, 1), (8, 9, 100), (50, 3, 100)]:  # last: > 4096 candidates, global-memory path
         D = np.sort(rng.random((shards, nq, k), dtype=np.float32), axis=2)
         D[:, :, k // 2:] = np.round(D[:, :, k // 2:], 1)                      # force ties across shards
         D = np.sort(D, axis=2)
@@ -262,3 +262,27 @@ def test_filter_functor_is_a_per_call_delete_mask(lib, orc, graphs):
     # the filter does not stick to the index: the next plain search is bare-bone again
     bare = orc.hnsw_load(s["metric"], s["d"], s["path"]).search(s["Q"], 10, 64)
     _check(idx.searchKnnBatch(s["Q"], 10, ef=64), bare, "after filter")
+
+
+def test_pipelined_shard_search_single_rank(lib, graphs):
+    """sharded.PipelinedShardSearch (exchange of batch i on a side stream under the search of batch i+1): with one
+    rank the exchange is the identity merge, so every submitted batch must equal the plain batched search, also when
+    the double-buffered result blocks are reused."""
+    import torch
+    from research_new_hnsw_b200.sharded import PipelinedShardSearch
+    s = graphs["l2_d128"]
+    idx = lib.HierarchicalNSW(lib.L2Space(s["d"]), s["path"])
+    Q = s["Q"]
+    halves = [Q[: len(Q) // 2], Q[len(Q) // 2: 2 * (len(Q) // 2)]]
+    want = [idx.searchKnnBatch(h, 10, ef=48) for h in halves]
+    dq = [torch.from_numpy(np.ascontiguousarray(h)).cuda() for h in halves]
+    pipe = PipelinedShardSearch(idx, len(halves[0]), 10, torch.device("cuda", 0), depth=2)
+    got = []
+    for step in range(6):
+        ol, od, ev = pipe.submit(dq[step % 2].data_ptr(), 48)
+        ev.synchronize()
+        got.append((step % 2, ol.cpu().numpy().view(np.uint64).copy(), od.cpu().numpy().copy()))
+    pipe.drain()
+    torch.cuda.synchronize()
+    for which, l, d in got:
+        assert np.array_equal(l, want[which]["labels"]) and np.array_equal(d, want[which]["dists"])
