@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--metric", default="l2", choices=["l2", "ip"],
                     help="l2 = C2 (SIFT-shaped); ip = C3-style shards (Deep-shaped: unit-norm rows, inner product)")
+    ap.add_argument("--parallel", default="shard", choices=["shard", "replica"],
+                    help="N > 1: 'shard' = one sub-index per GPU + all_gather/merge (north_star); 'replica' = the same "
+                         "index on every GPU, each GPU serving its own query batches (no exchange)")
     ap.add_argument("--storage", default="f32", choices=["f32", "bf16"],
                     help="device copy of the vectors: f32 (default, reference-exact traversal) or bf16 traversal + f32 re-rank")
     return ap.parse_args()
@@ -266,9 +269,17 @@ def run_b200(a, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     threads = max(1, (os.cpu_count() or 1) // world)
-    X = shard_data(a, rank)
-    batches = query_batches(a)
-    shard_labels = np.arange(a.n, dtype=np.uint64) + np.uint64(rank * a.n)
+    replica = world > 1 and a.parallel == "replica"
+    sw = 1 if replica else world                    # ranks that exchange results (1: no data-path collective)
+    drank = 0 if replica else rank
+    X = shard_data(a, drank)
+    if replica:  # every replica serves its own queries
+        from research_new_hnsw_b200.synth import lowrank_data
+        batches = [lowrank_data(a.nq, a.dim, seed=2 + 7 * b + 1000 * rank, normalize=(a.metric == "ip"))
+                   for b in range(max(1, a.batches))]
+    else:
+        batches = query_batches(a)
+    shard_labels = np.arange(a.n, dtype=np.uint64) + np.uint64(drank * a.n)
     if world == 1:
         # the graph both arms search: built by the reference on the host cores, loaded from its saveIndex file
         path, build_s = build_graph_with_reference(a, rank, X, threads)
@@ -298,6 +309,8 @@ def run_b200(a, rank, local_rank, world):
 
     from research_new_hnsw_b200.sharded import ShardedSearcher, cuda_merge
     sharded = ShardedSearcher(None, cuda_merge(lambda: stream), device=dev)
+    if replica:
+        sharded.world = 1
 
     def merged(labels_t, dists_t, nq):
         """all_gather per-shard rows + GPU k-way merge; identity at world == 1."""
@@ -310,7 +323,7 @@ def run_b200(a, rank, local_rank, world):
     gt = gt_l.cpu().numpy().view(np.uint64)
 
     from research_new_hnsw_b200.sharded import PackedShardExchange
-    packed = PackedShardExchange(a.nq, a.k, dev) if world > 1 else None
+    packed = PackedShardExchange(a.nq, a.k, dev) if sw > 1 else None
 
     def dev_search(dQ, nq, ef, work=None):
         if packed is not None and nq == a.nq:
@@ -347,7 +360,7 @@ def run_b200(a, rank, local_rank, world):
         works.append(w.cpu().numpy().astype(np.int64))
     from research_new_hnsw_b200.sharded import PipelinedShardSearch
     pipe = None
-    if world > 1 and not os.environ.get("B200HNSW_BENCH_NO_PIPELINE"):
+    if sw > 1 and not os.environ.get("B200HNSW_BENCH_NO_PIPELINE"):
         pipe = PipelinedShardSearch(idx, a.nq, a.k, dev, depth=int(os.environ.get("B200HNSW_PIPE_DEPTH", "2")))
     for s in range(a.warmup):
         if pipe is not None:
@@ -435,7 +448,7 @@ def run_b200(a, rank, local_rank, world):
     dq_buf = torch.empty((a.nq, a.dim), dtype=torch.float32, device=dev)
 
     def e2e_step(s):
-        if world == 1:  # the reference-facing host-pointer C ABI: H2D + kernel + D2H inside the call
+        if sw == 1:  # the reference-facing host-pointer C ABI: H2D + kernel + D2H inside the call
             idx.searchKnnBatch(hq[s % len(hq)].numpy(), a.k, ef=ef, out=hout)
         else:  # sharded public API: pinned H2D -> per-shard search -> all_gather + merge -> D2H of the merged rows
             dq_buf.copy_(hq[s % len(hq)], non_blocking=True)
@@ -506,6 +519,8 @@ def run_b200(a, rank, local_rank, world):
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
                        "storage": a.storage, "ef_table": ef_table,
                        "parallelism": "1 GPU" if world == 1 else
+                       ("replica%d: the same %d-point index on every GPU, each GPU serves its own query batches, no "
+                        "data-path collective" % (world, a.n)) if replica else
                        "shard%d: one %d-point sub-index per GPU, queries replicated, ONE packed NCCL all_gather + GPU merge "
                        "per batch%s; value counts shard-level searches (merged queries/s = value/%d)"
                        % (world, a.n, ", exchange of batch i overlapped with the search of batch i+1" if pipe else "", world),
@@ -516,9 +531,9 @@ def run_b200(a, rank, local_rank, world):
             "clocks": clocks, "per_rank": rank_diag,
             "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
-                    "api": "b200hnsw_search_batch (host pointers, pinned)" if world == 1 else
+                    "api": "b200hnsw_search_batch (host pointers, pinned)" if sw == 1 else
                            "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},
-            "gpu_launches": a.steps * (1 if world == 1 else 2),  # search kernel (+ merge kernel at N > 1)
+            "gpu_launches": a.steps * (1 if sw == 1 else 2),  # search kernel (+ merge kernel at N > 1)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "hnsw_search_kernel<team %d, %s>" % (64 if a.nq >= 2368 else 128, a.metric), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src,

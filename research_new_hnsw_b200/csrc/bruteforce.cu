@@ -4,7 +4,7 @@
 #include <vector>
 
 #include "bruteforce.cuh"
-#include "search_kernel.cuh"  // merge_topk_kernel
+#include "merge_launch.cuh"
 
 namespace b200 {
 
@@ -236,7 +236,7 @@ __global__ void bf_pad_rows_kernel(const float *__restrict__ X, uint32_t dim, ui
 BruteIndex::~BruteIndex() {
     tz.release();
     cudaFree(dX); cudaFree(dLabels); cudaFree(dQ); cudaFree(dOutL); cudaFree(dOutD); cudaFree(dPartL);
-    cudaFree(dPartD); cudaFree(dCounts);
+    cudaFree(dPartD); cudaFree(dPart2L); cudaFree(dPart2D); cudaFree(dCounts);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -366,6 +366,16 @@ int BruteIndex::remove(uint64_t label) {
     return 0;
 }
 
+int BruteIndex::ensure_part2(size_t elems) {
+    if (elems <= part2_elems) return 0;
+    cudaFree(dPart2L); cudaFree(dPart2D);
+    dPart2L = nullptr; dPart2D = nullptr; part2_elems = 0;
+    B200_CUDA_OK(cudaMalloc(&dPart2L, elems * 8));
+    B200_CUDA_OK(cudaMalloc(&dPart2D, elems * 4));
+    part2_elems = elems;
+    return 0;
+}
+
 int BruteIndex::ensure_part(size_t elems) {
     if (elems <= part_elems) return 0;
     cudaFree(dPartL); cudaFree(dPartD);
@@ -377,7 +387,8 @@ int BruteIndex::ensure_part(size_t elems) {
 }
 
 // Path choice: the tensor-core candidate generator pays off once the scan is a real GEMM (rows x queries large);
-// small problems and anything it cannot bound go to the exact scan.  B200HNSW_BF_PATH=scan|tensor forces one.
+// a few queries over many rows stream the rows once (bf_stream.cu); everything else, and anything those two cannot
+// take, goes to the tiled exact scan.  B200HNSW_BF_PATH=scan|tensor|stream forces one.
 int BruteIndex::search_device(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc,
                               cudaStream_t st) {
     if (nq == 0) return 0;
@@ -386,10 +397,15 @@ int BruteIndex::search_device(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const char *force = getenv("B200HNSW_BF_PATH");
     const bool want_scan = force && !strcmp(force, "scan");
     const bool want_tensor = force && !strcmp(force, "tensor");
+    const bool want_stream = force && !strcmp(force, "stream");
     const size_t n = host.cur;
-    if (!want_scan && k <= n && (want_tensor || (double)n * (double)nq >= 6.7e7)) {
+    if (!want_scan && !want_stream && k <= n && (want_tensor || (double)n * (double)nq >= 6.7e7)) {
         const int rc = search_tensor(dQ_, nq, k, dl, dd, dc, st);
         if (rc <= 0) { last_path = 1; return rc; }  // done, or a real error; rc == 1 -> fall through to the scan
+    }
+    if (!want_scan && (want_stream || (nq <= 64 && n >= 16384))) {
+        const int rc = search_stream(dQ_, nq, k, dl, dd, dc, st);
+        if (rc <= 0) { last_path = 2; return rc; }  // rc == 1: shape does not fit the streaming kernel
     }
     last_path = 0;
     return search_scan(dQ_, nq, k, dl, dd, dc, st);
@@ -437,12 +453,12 @@ int BruteIndex::search_scan(const float *dQ_, size_t nq, size_t k, uint64_t *dl,
                                                              (uint32_t)nq, (uint32_t)k, (uint32_t)rows_per_slice,
                                                              dPartD, dPartL);
     B200_CUDA_OK(cudaGetLastError());
-    const unsigned warps = 4;
-    merge_topk_kernel<<<(unsigned)((nq + warps - 1) / warps), warps * 32, 0, st>>>(
-        dPartL, dPartD, nq * k, nq * k, (uint32_t)slices, (uint32_t)nq, (uint32_t)k, dl, dd);
-    B200_CUDA_OK(cudaGetLastError());
+    rc = ensure_part2(merge_tree_scratch(slices, nq, k));
+    if (rc) return rc;
+    unsigned merges = 0;
+    B200_CUDA_OK(merge_tree(dPartL, dPartD, slices, nq, k, dPart2L, dPart2D, dl, dd, st, &merges));
     if (dc) bf_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(dc, (uint32_t)nq, (uint32_t)std::min(k, n));
-    stats.kernel_launches += 2;
+    stats.kernel_launches += 1 + merges;
     return 0;
 }
 

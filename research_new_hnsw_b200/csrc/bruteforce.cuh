@@ -36,13 +36,13 @@ struct BruteIndex {
     std::mutex mu;
     b200hnsw_stats stats{};
     BruteTensor tz;
-    int last_path = 0;  // 0 = exact scan, 1 = tensor-core candidates + exact re-rank
+    int last_path = 0;  // 0 = tiled exact scan, 1 = tensor-core candidates + exact re-rank, 2 = streaming exact scan
     // scratch
     float *dQ = nullptr;
-    uint64_t *dOutL = nullptr, *dPartL = nullptr;
-    float *dOutD = nullptr, *dPartD = nullptr;
+    uint64_t *dOutL = nullptr, *dPartL = nullptr, *dPart2L = nullptr;
+    float *dOutD = nullptr, *dPartD = nullptr, *dPart2D = nullptr;
     uint32_t *dCounts = nullptr;
-    size_t scratch_q = 0, scratch_k = 0, part_elems = 0;
+    size_t scratch_q = 0, scratch_k = 0, part_elems = 0, part2_elems = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
@@ -60,6 +60,9 @@ struct BruteIndex {
     int tensor_sync_rows(size_t first, size_t count);
     int search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
     int search_scan(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
+    // bf_stream.cu
+    int search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
+    int ensure_part2(size_t elems);
 };
 
 }  // namespace b200

@@ -5,6 +5,7 @@
 
 #include "bruteforce.cuh"
 #include "hnsw_index.cuh"
+#include "merge_launch.cuh"
 
 struct b200hnsw_index { b200::HnswIndex ix; };
 struct b200bf_index { b200::BruteIndex ix; };
@@ -301,17 +302,7 @@ static int merge_launch(const uint64_t *l, const float *d, size_t ls, size_t ds,
         return B200HNSW_E_ARG;
     }
     if (nq == 0) return 0;
-    const size_t total = shards * k;
-    unsigned warps = 4;
-    while (warps > 1 && warps * total * 12 > 48 * 1024) warps >>= 1;
-    const unsigned grid = (unsigned)((nq + warps - 1) / warps);
-    if (warps * total * 12 <= 48 * 1024)
-        b200::merge_topk_smem_kernel<<<grid, warps * 32, warps * total * 12, (cudaStream_t)cuda_stream>>>(
-            l, d, ls, ds, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, ol, od);
-    else  // more than 4096 candidates per query: read them from global memory
-        b200::merge_topk_kernel<<<grid, warps * 32, 0, (cudaStream_t)cuda_stream>>>(
-            l, d, ls, ds, (uint32_t)shards, (uint32_t)nq, (uint32_t)k, ol, od);
-    B200_CUDA_OK(cudaGetLastError());
+    B200_CUDA_OK(b200::merge_level(l, d, ls, ds, shards, shards, nq, k, ol, od, 0, 0, (cudaStream_t)cuda_stream));
     return 0;
 }
 

@@ -689,23 +689,31 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
     }
 }
 
-// k-way merge of per-shard results: one warp per query over shards*k candidates.  Shard s holds its
-// rows at labels_in + s*lstride / dists_in + s*dstride (elements), so the per-shard blocks may be packed
-// [labels | dists] and exchanged with ONE all_gather.
+// k-way merge of per-shard results: one warp per query over the candidates of one GROUP of shards.
+// Shard s holds its rows at labels_in + s*lstride / dists_in + s*dstride (elements), so per-shard blocks may be packed
+// [labels | dists] and exchanged with ONE all_gather.  blockIdx.y selects the group of `group` consecutive shards and
+// the output list at labels_out + blockIdx.y*ols / dists_out + blockIdx.y*ods (merge_launch.cuh builds the tree).
+// Candidates are ranked by (dist, label, position).  This version reads every pair from global memory (total^2
+// dependent loads per warp): only used beyond 4096 candidates per warp.
 static __global__ void merge_topk_kernel(const uint64_t *__restrict__ labels_in, const float *__restrict__ dists_in,
-                                         size_t lstride, size_t dstride, uint32_t shards, uint32_t nq, uint32_t k,
-                                         uint64_t *__restrict__ labels_out, float *__restrict__ dists_out) {
+                                         size_t lstride, size_t dstride, uint32_t shards, uint32_t group, uint32_t nq,
+                                         uint32_t k, uint64_t *__restrict__ labels_out, float *__restrict__ dists_out,
+                                         size_t ols, size_t ods) {
     const uint32_t qi = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (qi >= nq) return;
-    const uint32_t total = shards * k;
-    // rank of every candidate among all candidates by (dist, label); O(total^2/32) per warp, total <= 8*100
+    const uint32_t s0 = blockIdx.y * group;
+    const uint32_t total = min(group, shards - s0) * k;
+    labels_in += (size_t)s0 * lstride;
+    dists_in += (size_t)s0 * dstride;
+    labels_out += (size_t)blockIdx.y * ols;
+    dists_out += (size_t)blockIdx.y * ods;
     for (uint32_t c = lane; c < total; c += 32) {
         const uint32_t s = c / k, j = c % k;
         const float dc = dists_in[s * dstride + (size_t)qi * k + j];
         const uint64_t lc = labels_in[s * lstride + (size_t)qi * k + j];
         uint32_t rank = 0;
-        for (uint32_t o = 0; o < total; o++) {
+        for (uint32_t o = 0; o < total && rank < k; o++) {
             const uint32_t so = o / k, jo = o % k;
             const float d2 = dists_in[so * dstride + (size_t)qi * k + jo];
             const uint64_t l2 = labels_in[so * lstride + (size_t)qi * k + jo];
@@ -719,20 +727,27 @@ static __global__ void merge_topk_kernel(const uint64_t *__restrict__ labels_in,
 }
 
 // Same contract, candidates staged once into shared memory (coalesced per-shard row reads), ranks computed from
-// shared memory with broadcast reads: the global-memory version above is latency-bound (total^2 dependent loads per
-// warp) and, on a high-priority exchange stream, crowds the search kernel out of the SMs.  Dynamic shared memory:
-// warps_per_cta * total * 12 bytes.
+// shared memory with broadcast reads and an early exit once a candidate's rank reaches k.  The global-memory version
+// is latency-bound and, on a high-priority exchange stream, crowds the search kernel out of the SMs.  Dynamic shared
+// memory: warps_per_cta * group * k * 12 bytes.
 static __global__ void merge_topk_smem_kernel(const uint64_t *__restrict__ labels_in, const float *__restrict__ dists_in,
-                                              size_t lstride, size_t dstride, uint32_t shards, uint32_t nq, uint32_t k,
-                                              uint64_t *__restrict__ labels_out, float *__restrict__ dists_out) {
+                                              size_t lstride, size_t dstride, uint32_t shards, uint32_t group,
+                                              uint32_t nq, uint32_t k, uint64_t *__restrict__ labels_out,
+                                              float *__restrict__ dists_out, size_t ols, size_t ods) {
     extern __shared__ __align__(16) unsigned char merge_smem[];
     const uint32_t warps = blockDim.x / 32, w = threadIdx.x / 32;
     const uint32_t qi = blockIdx.x * warps + w;
     const int lane = threadIdx.x & 31;
     if (qi >= nq) return;
-    const uint32_t total = shards * k;
-    uint64_t *sl = reinterpret_cast<uint64_t *>(merge_smem) + (size_t)w * total;
-    float *sd = reinterpret_cast<float *>(merge_smem + (size_t)warps * total * 8) + (size_t)w * total;
+    const uint32_t s0 = blockIdx.y * group;
+    const uint32_t cap = min(group, shards) * k;            // per-warp slice of the shared arrays
+    const uint32_t total = min(group, shards - s0) * k;
+    labels_in += (size_t)s0 * lstride;
+    dists_in += (size_t)s0 * dstride;
+    labels_out += (size_t)blockIdx.y * ols;
+    dists_out += (size_t)blockIdx.y * ods;
+    uint64_t *sl = reinterpret_cast<uint64_t *>(merge_smem) + (size_t)w * cap;
+    float *sd = reinterpret_cast<float *>(merge_smem + (size_t)warps * cap * 8) + (size_t)w * cap;
     for (uint32_t c = lane; c < total; c += 32) {
         const uint32_t s = c / k, j = c % k;
         sl[c] = labels_in[s * lstride + (size_t)qi * k + j];
@@ -745,9 +760,9 @@ static __global__ void merge_topk_smem_kernel(const uint64_t *__restrict__ label
         uint32_t rank = 0;
         for (uint32_t o = 0; o < total; o++) {
             const float d2 = sd[o];
-            // ties on distance are rare: only then look at the label
-            if (d2 < dc) rank++;
-            else if (d2 == dc) {
+            if (d2 < dc) {
+                rank++;
+            } else if (d2 == dc) {  // ties on distance are rare: only then look at the label
                 const uint64_t l2 = sl[o];
                 rank += (l2 < lc || (l2 == lc && o < c)) ? 1u : 0u;
             }

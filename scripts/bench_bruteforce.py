@@ -52,13 +52,38 @@ try:
            "dists_bit_equal": bool(np.array_equal(rr["dists"], r["dists"][:64]))}
 except Exception as e:
     cpu = {"value": None, "sample": "unavailable: %s" % e}
+# small-batch regime (nq = 1 and 128 next to the headline): one pass over the rows is the floor
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+hbm = peaks.get("hbm_gbs", 6550.0)
+small = []
+for nq_s in (1, 4, 8, 16, 32, 64, 128, 1024):
+    for path in ("auto", "stream", "tensor"):
+        if path == "stream" and nq_s > 128: continue
+        if path == "tensor" and nq_s < 16: continue
+        if path == "auto": os.environ.pop("B200HNSW_BF_PATH", None)
+        else: os.environ["B200HNSW_BF_PATH"] = path
+        for _ in range(2): g.searchKnnDevice(dQ[0].data_ptr(), nq_s, a.k, ol.data_ptr(), od.data_ptr(), 0, stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for it in range(5): g.searchKnnDevice(dQ[it % 2].data_ptr(), nq_s, a.k, ol.data_ptr(), od.data_ptr(), 0, stream)
+        e1.record(); torch.cuda.synchronize()
+        ms_s = e0.elapsed_time(e1) / 5
+        small.append({"nq": nq_s, "path": path, "ms": round(ms_s, 4), "qps": round(nq_s / (ms_s * 1e-3), 1),
+                      "hbm_frac_one_pass": round(4.0 * a.n * a.dim / (ms_s * 1e-3) / 1e9 / hbm, 3)})
+os.environ.pop("B200HNSW_BF_PATH", None)
+# exactness of the small-batch paths against the tiled exact scan
+rq = g.searchKnnBatch(Qs[0][:16], a.k)
+os.environ["B200HNSW_BF_PATH"] = "scan"
+rq2 = g.searchKnnBatch(Qs[0][:16], a.k)
+os.environ.pop("B200HNSW_BF_PATH", None)
+small_ok = bool(np.array_equal(rq["labels"], rq2["labels"]) and np.array_equal(rq["dists"], rq2["dists"]))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
 flops = 2.0 * a.nq * a.n * a.dim
 print(json.dumps({"metric": "BruteforceSearch exact k=%d QPS, %dx%d inner product" % (a.k, a.n, a.dim), "value": a.nq / (ms * 1e-3),
     "unit": "queries/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
     "dtype": "bf16 candidates + f32 exact re-rank", "data": "synthetic",
     "config": {"workload": "C4: %dx%d unit-norm rank-64+noise rows, IP, k=%d, %d queries per batch" % (a.n, a.dim, a.k, a.nq),
-               "exact_scan_parity_512_queries": scan_ok},
+               "exact_scan_parity_512_queries": scan_ok, "small_batches": small, "small_batch_parity_16_queries": small_ok},
     "e2e": {"value": a.nq / e2e, "unit": "queries/s", "h2d_bytes_per_step": a.nq * a.dim * 4, "d2h_bytes_per_step": a.nq * a.k * 12 + a.nq * 4},
     "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                  "frac": flops / (ms * 1e-3) / 1e12 / peak, "traffic": None,

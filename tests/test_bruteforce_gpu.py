@@ -97,3 +97,55 @@ def test_tensor_core_path_is_exact(lib, orc, monkeypatch, metric, n, d, k, nq):
     assert g.stats()["hops_base"] == 0
     assert np.array_equal(rg["labels"], rs["labels"]) and np.array_equal(rg["dists"], rs["dists"])
     assert np.array_equal(rg["counts"], rs["counts"])
+
+
+@pytest.mark.parametrize("metric,n,d,k", [(bind.L2, 5000, 128, 10), (bind.IP, 3001, 96, 100), (bind.L2, 2000, 30, 7),
+                                          (bind.IP, 1500, 17, 3), (bind.L2, 700, 3, 5), (bind.IP, 4097, 768, 100),
+                                          (bind.L2, 20000, 100, 1), (bind.IP, 50, 768, 100)])
+def test_streaming_path_is_exact(lib, orc, monkeypatch, metric, n, d, k):
+    """Small query batches stream the rows once (csrc/bf_stream.cu: bulk-copy ring, lane = row, the reference's SSE
+    summation order): ids and distances bit-identical to the oracle for every pass shape (1, 2, 4, 8, 16 queries per
+    pass, several passes), ragged last row tile, dims with sequential tails, duplicate rows, k > count."""
+    monkeypatch.setenv("B200HNSW_BF_PATH", "stream")
+    X = gauss(61, n, d)
+    if metric == bind.IP:
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+    X[n // 2] = X[n // 3]
+    labels = (np.arange(n, dtype=np.uint64) * 5 + 2)
+    space = lib.L2Space(d) if metric == bind.L2 else lib.InnerProductSpace(d)
+    g = lib.BruteforceSearch(space, n)
+    g.addPoints(X, labels)
+    c = orc.bf_new(metric, d, n)
+    c.add(X, labels)
+    Qall = gauss(62, 41, d)
+    Qall[0] = X[n // 3]                                        # query equal to the duplicated rows: an exact tie
+    for nq in (1, 2, 3, 5, 8, 9, 16, 17, 41):
+        Q = Qall[:nq]
+        rg, rc = g.searchKnnBatch(Q, k), c.search(Q, k)
+        assert g.stats()["hops_base"] == 2, "streaming path did not run"
+        assert np.array_equal(rg["labels"], rc["labels"]), (nq,)
+        assert np.array_equal(rg["dists"], rc["dists"]), (nq,)
+        assert np.array_equal(rg["counts"], rc["counts"])
+
+
+def test_partial_merge_tree_many_slices(lib, orc, monkeypatch):
+    """Per-CTA partial lists are reduced by merge_launch.cuh: 64 slices x k=100 (tiled scan) and 148 x 100 (streaming
+    scan) take the one-CTA-per-query selection kernel, 148 x 200 = 29 600 candidates the multi-level tree."""
+    monkeypatch.setenv("B200HNSW_BF_PATH", "scan")
+    n, d, k = 300_000, 16, 100
+    X = gauss(71, n, d)
+    Q = gauss(72, 70, d)
+    g = lib.BruteforceSearch(lib.L2Space(d), n)
+    g.addPoints(X)
+    c = orc.bf_new(bind.L2, d, n)
+    c.add(X)
+    rg, rc = g.searchKnnBatch(Q, k), c.search(Q[:8], k)
+    assert g.stats()["hops_base"] == 0
+    assert np.array_equal(rg["labels"][:8], rc["labels"]) and np.array_equal(rg["dists"][:8], rc["dists"])
+    monkeypatch.setenv("B200HNSW_BF_PATH", "stream")
+    rs = g.searchKnnBatch(Q, k)
+    assert np.array_equal(rg["labels"], rs["labels"]) and np.array_equal(rg["dists"], rs["dists"])
+    k2 = 200                                                     # too many candidates for the selection kernel
+    rt, rc2 = g.searchKnnBatch(Q[:5], k2), c.search(Q[:5], k2)
+    assert g.stats()["hops_base"] == 2
+    assert np.array_equal(rt["labels"], rc2["labels"]) and np.array_equal(rt["dists"], rc2["dists"])
