@@ -6,18 +6,19 @@
 // rows, at most 64 CTAs for one query tile) and cannot stream: this kernel is the streaming one.
 //
 //   * persistent grid, one CTA per SM, CTA b walks row tiles b, b+grid, ... of 64 rows;
-//   * one producer lane moves 64 rows x 512 B per stage with four 8 KB TMA box loads (cp.async.bulk.tensor.2d over
-//     the fp32 rows, 128-byte swizzle, completion on an mbarrier) into a 4-stage ring; the swizzle spreads the eight
-//     16 B chunks of a 128 B row segment over the banks by row, so lane = row reads are conflict-free without padding
-//     (a first version used one 512 B 1-D bulk copy per row: 64 small TMA operations per stage capped it at 0.7 TB/s);
+//   * a producer warp moves 64 rows x 512 B per stage with 16-byte cp.async copies (one warp instruction = 512
+//     contiguous bytes of one row, completion on an mbarrier via cp.async.mbarrier.arrive) into a 4-stage ring laid out
+//     like a 128-byte-swizzled TMA tile: the eight 16 B chunks of a 128 B row segment are XOR-ed with the row number,
+//     so lane = row reads are conflict-free without padding.  Measured alternatives on 1M x 768, one query: one 512 B
+//     1-D bulk copy (cp.async.bulk) per row 4.5 ms (64 small TMA operations per stage); four 64-row x 128 B swizzled
+//     2-D TMA boxes per stage 0.84 ms; this LDGSTS producer 0.86 ms -- the last two are bound by the compute warps,
+//     not by the copy engine;
 //   * compute thread = (row of the tile, query slot): it owns the four lane accumulators + sequential tail of the
 //     reference's SSE kernels for P queries (space_l2.h:97-143, space_ip.h:255-303: separate multiply and add,
 //     ((s0+s1)+s2)+s3 + tail) -- query chunks are broadcast reads, so distances are bit-identical to the CPU;
 //   * per row tile, distances not worse than the query's current k-th are pushed to a small shared queue and one
 //     warp per query folds the queue into that query's unsorted k-best list (replace-worst, ordered by (dist,label));
 //   * every CTA writes its k best per query; merge_tree() (merge_launch.cuh) reduces the per-CTA lists.
-#include <cuda.h>
-
 #include <algorithm>
 #include <cstring>
 
@@ -31,8 +32,6 @@ constexpr int kStKC4 = 32;                      // 128-bit chunks per row per st
 constexpr int kStStages = 4;
 constexpr int kStBoxBytes = kStRows * 128;      // one TMA box: 64 rows x 32 floats
 constexpr int kStStageBytes = kStRows * kStKC4 * 16;
-
-int make_map_f32(void *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows);
 
 struct StreamSmem {
     uint32_t off_stage, off_q, off_topl, off_topd, off_ql, off_qd, off_meta, total;
@@ -68,13 +67,13 @@ __device__ __forceinline__ void st_mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(st_smem_u32(bar)), "r"(parity) : "memory");
 }
-// TMA box load (2-D tiled map) global -> shared, completion (bytes) signalled on an mbarrier
-__device__ __forceinline__ void st_tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            st_smem_u32(dst)),
-        "l"((uint64_t)map), "r"(st_smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
+// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only; completion is attached to an mbarrier below
+__device__ __forceinline__ void st_cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async copies have landed
+__device__ __forceinline__ void st_cp_async_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(st_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool st_pair_less(float d1, uint64_t l1, float d2, uint64_t l2) {
     return d1 < d2 || (d1 == d2 && l1 < l2);
@@ -92,11 +91,11 @@ __device__ __forceinline__ float st_term(float q, float x) {
 // QS query slots x P queries per slot = queries per pass; 64*QS compute threads + one producer warp.
 template <int METRIC, int QS, int P>
 __global__ void __launch_bounds__(64 * QS + 32, 1)
-    bf_stream_kernel(const __grid_constant__ CUtensorMap tmX, const uint64_t *__restrict__ labels, uint32_t n, uint32_t d4,
+    bf_stream_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels, uint32_t n, uint32_t d4,
                      uint32_t lane_chunks, uint32_t dim, const float *__restrict__ Q, uint32_t nq, uint32_t k,
                      float *__restrict__ part_d, uint64_t *__restrict__ part_l) {
     constexpr int NQT = QS * P, NCOMP = 64 * QS, NCW = NCOMP / 32;
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[kStStages], empty[kStStages];
     const StreamSmem L(NQT, d4, k);
     unsigned char *ring = smem + ((1024u - (st_smem_u32(smem) & 1023u)) & 1023u);  // 128-byte swizzle needs 1024 B alignment
@@ -114,7 +113,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
 
     if (tid == 0) {
         for (int s = 0; s < kStStages; s++) {
-            st_mbar_init(full + s, 1);
+            st_mbar_init(full + s, 32);  // one deferred arrival per producer lane
             st_mbar_init(empty + s, NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,21 +135,23 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
     __syncthreads();
 
     if (warp == NCW) {
-        // ---- producer: one lane issues the TMA loads
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (uint32_t kc = 0; kc < nkc; kc++, it++) {
-                    const uint32_t s = it % kStStages, ph = (it / kStStages) & 1;
-                    const uint32_t c4 = min((uint32_t)kStKC4, d4 - kc * kStKC4);
-                    const uint32_t boxes = (c4 + 7) / 8;  // rows / columns out of bounds are zero-filled
-                    st_mbar_wait(empty + s, ph ^ 1);
-                    st_mbar_expect_tx(full + s, boxes * kStBoxBytes);
-                    unsigned char *base = ring + s * kStStageBytes;
-                    for (uint32_t b = 0; b < boxes; b++)
-                        st_tma_load_2d(base + b * kStBoxBytes, &tmX, full + s, (int)((kc * kStKC4 + b * 8) * 4),
-                                       (int)(tile * kStRows));
+        // ---- producer warp: lane = 16-byte chunk of the stage's 512-byte row segment
+        uint32_t it = 0;
+        const uint32_t slot = (uint32_t)(lane >> 3) * kStBoxBytes;
+        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const uint32_t rows = min((uint32_t)kStRows, n - tile * kStRows);
+            for (uint32_t kc = 0; kc < nkc; kc++, it++) {
+                const uint32_t s = it % kStStages, ph = (it / kStStages) & 1;
+                const uint32_t ci = kc * kStKC4 + lane;
+                st_mbar_wait(empty + s, ph ^ 1);
+                if (ci < d4) {  // rows / chunks past the end are never read by the compute threads
+                    unsigned char *dst = ring + s * kStStageBytes + slot;
+                    const float4 *src = X + (size_t)tile * kStRows * d4 + ci;
+#pragma unroll 8
+                    for (uint32_t r = 0; r < rows; r++)
+                        st_cp_async16(dst + r * 128 + (((uint32_t)(lane & 7) ^ (r & 7)) << 4), src + (size_t)r * d4);
                 }
+                st_cp_async_arrive(full + s);
             }
         }
         return;
@@ -158,6 +159,10 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
 
     // ---- compute threads
     const int r = tid & (kStRows - 1), qs = tid / kStRows;
+    const uint32_t sw = (uint32_t)(r & 7);
+    uint32_t xo[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) xo[j] = ((uint32_t)j ^ sw) << 4;
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         float acc[P][4], tail[P];
@@ -175,10 +180,27 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
             st_mbar_wait(full + s, ph);
             // chunk c of row r lives in box c/8 at 16-byte slot (c%8) ^ (r%8) of the row's 128-byte segment
             const unsigned char *sx = ring + s * kStStageBytes + r * 128;
-            const uint32_t sw = (uint32_t)(r & 7);
             const float4 *sq = sQ + (size_t)(qs * P) * d4 + base;
-#pragma unroll 4
-            for (uint32_t c = 0; c < nl; c++) {
+            // whole boxes inside the lane part: the eight slot offsets are per-thread constants (xo[]), so a chunk costs
+            // two LDS.128 + 8 FP instructions per query and no address arithmetic
+            const uint32_t nfull = nl >> 3;
+            for (uint32_t b = 0; b < nfull; b++) {
+                const unsigned char *bx = sx + b * kStBoxBytes;
+                const float4 *bq = sq + b * 8;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 x = *(const float4 *)(bx + xo[j]);
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        const float4 q = bq[(size_t)p * d4 + j];
+                        acc[p][0] = __fadd_rn(acc[p][0], st_term<METRIC>(q.x, x.x));
+                        acc[p][1] = __fadd_rn(acc[p][1], st_term<METRIC>(q.y, x.y));
+                        acc[p][2] = __fadd_rn(acc[p][2], st_term<METRIC>(q.z, x.z));
+                        acc[p][3] = __fadd_rn(acc[p][3], st_term<METRIC>(q.w, x.w));
+                    }
+                }
+            }
+            for (uint32_t c = nfull * 8; c < nl; c++) {
                 const float4 x = *(const float4 *)(sx + (c >> 3) * kStBoxBytes + (((c & 7) ^ sw) << 4));
 #pragma unroll
                 for (int p = 0; p < P; p++) {
@@ -288,7 +310,7 @@ __global__ void bf_stream_counts_kernel(uint32_t *counts, uint32_t nq, uint32_t 
 }
 
 template <int METRIC, int QS, int P>
-static cudaError_t stream_launch(dim3 grid, uint32_t smem_bytes, cudaStream_t st, const CUtensorMap &X, const uint64_t *labels,
+static cudaError_t stream_launch(dim3 grid, uint32_t smem_bytes, cudaStream_t st, const float4 *X, const uint64_t *labels,
                                  uint32_t n, uint32_t d4, uint32_t lane_chunks, uint32_t dim, const float *Q, uint32_t nq,
                                  uint32_t k, float *pd, uint64_t *pl) {
     cudaError_t e = cudaFuncSetAttribute(bf_stream_kernel<METRIC, QS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -313,8 +335,10 @@ int BruteIndex::search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *d
     }
     // static shared memory of the kernel: 2 * kStStages mbarriers
     const size_t budget = (size_t)smem_optin[di] - 2 * kStStages * 8 - 64;
-    // queries per pass: the largest of {16, 8, 4, 2, 1} that is useful and fits
-    static const int cfg_qs[5] = {8, 8, 4, 2, 1}, cfg_p[5] = {2, 1, 1, 1, 1};
+    // queries per pass: the largest of {16, 8, 4, 2, 1} that is useful and fits.  A row chunk read from shared memory
+    // serves the P queries of its thread, so P grows before the number of query slots does (with 8 slots x 1 query
+    // the rows were re-read 8 times and shared-memory bandwidth, not HBM, set the pace).
+    static const int cfg_qs[5] = {4, 4, 4, 2, 1}, cfg_p[5] = {4, 2, 1, 1, 1};
     int pick = -1;
     for (int c = 0; c < 5; c++) {
         const size_t nqt = (size_t)cfg_qs[c] * cfg_p[c];
@@ -339,20 +363,18 @@ int BruteIndex::search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *d
     else lane_floats = 0;
     const dim3 grid((unsigned)slices, (unsigned)passes);
     const int m = prm.metric == B200HNSW_L2 ? 0 : 1;
-    CUtensorMap tmX;
-    rc = make_map_f32(&tmX, dX, n, d4 * 4, d4 * 16, kStRows);
-    if (rc) return rc;
+
     cudaError_t e;
 #define B200_STREAM_CASE(QS_, P_)                                                                                       \
-    e = m == 0 ? stream_launch<0, QS_, P_>(grid, smem_bytes, st, tmX, dLabels, (uint32_t)n, (uint32_t)d4,                \
+    e = m == 0 ? stream_launch<0, QS_, P_>(grid, smem_bytes, st, dX, dLabels, (uint32_t)n, (uint32_t)d4,                \
                                            (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_, (uint32_t)nq, (uint32_t)k,  \
                                            dPartD, dPartL)                                                              \
-               : stream_launch<1, QS_, P_>(grid, smem_bytes, st, tmX, dLabels, (uint32_t)n, (uint32_t)d4,                \
+               : stream_launch<1, QS_, P_>(grid, smem_bytes, st, dX, dLabels, (uint32_t)n, (uint32_t)d4,                \
                                            (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_, (uint32_t)nq, (uint32_t)k,  \
                                            dPartD, dPartL)
     switch (pick) {
-        case 0: B200_STREAM_CASE(8, 2); break;
-        case 1: B200_STREAM_CASE(8, 1); break;
+        case 0: B200_STREAM_CASE(4, 4); break;
+        case 1: B200_STREAM_CASE(4, 2); break;
         case 2: B200_STREAM_CASE(4, 1); break;
         case 3: B200_STREAM_CASE(2, 1); break;
         default: B200_STREAM_CASE(1, 1); break;

@@ -607,22 +607,6 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t kp
     return 0;
 }
 
-// 2-D fp32 tensor [rows][cols], cols contiguous with a row pitch in bytes, box = 32 floats (128 B) x box_rows,
-// 128-byte swizzle, zero fill out of bounds (bf_stream.cu).
-int make_map_f32(void *map, const void *base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return B200HNSW_E_CUDA; }
-    cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {pitch_bytes};
-    cuuint32_t box[2] = {32, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc((CUtensorMap *)map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32 rows) failed"); return B200HNSW_E_CUDA; }
-    return 0;
-}
-
 void BruteTensor::release() {
     cudaFree(xb); cudaFree(xn2); cudaFree(qb); cudaFree(qn2); cudaFree(thr); cudaFree(tabB); cudaFree(tabT);
     cudaFree(panelmin); cudaFree(cand);

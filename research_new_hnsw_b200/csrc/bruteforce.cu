@@ -399,7 +399,10 @@ int BruteIndex::search_device(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const bool want_tensor = force && !strcmp(force, "tensor");
     const bool want_stream = force && !strcmp(force, "stream");
     const size_t n = host.cur;
-    if (!want_scan && !want_stream && k <= n && (want_tensor || (double)n * (double)nq >= 6.7e7)) {
+    // measured on 1M x 768 (scripts/bench_bruteforce.py): streaming wins up to 8 queries, the tensor path (one 256-query
+    // tile, ~1.4 ms) from there on; on small indexes its fixed cost (a dozen launches) is not worth it
+    const bool tensor_pays = (double)n * (double)nq >= 6.7e7 || (nq > 8 && n >= 131072);
+    if (!want_scan && !want_stream && k <= n && (want_tensor || tensor_pays)) {
         const int rc = search_tensor(dQ_, nq, k, dl, dd, dc, st);
         if (rc <= 0) { last_path = 1; return rc; }  // done, or a real error; rc == 1 -> fall through to the scan
     }
