@@ -457,13 +457,33 @@ def run_b200(a, rank, local_rank, world):
             pd.copy_(od_, non_blocking=True)
             torch.cuda.synchronize()
 
-    for s in range(3):
-        e2e_step(s)
+    if pipe is not None:
+        # sharded serving loop: two batches in flight; H2D, search, exchange and D2H of consecutive batches overlap
+        # (PipelinedShardSearch.submit_host).  Every step still copies its queries in and its merged rows out.
+        hl2 = [torch.empty((a.nq, a.k), dtype=torch.int64).pin_memory() for _ in range(2)]
+        hd2 = [torch.empty((a.nq, a.k), dtype=torch.float32).pin_memory() for _ in range(2)]
+        pend = [None, None]
+
+        def e2e_loop(steps):
+            for s in range(steps):
+                j = s % 2
+                if pend[j] is not None:
+                    pend[j].synchronize()             # the host consumes batch s-2 before its buffers are reused
+                pend[j] = pipe.submit_host(hq[s % len(hq)], ef, hl2[j], hd2[j])
+            for e in pend:
+                if e is not None:
+                    e.synchronize()
+            torch.cuda.synchronize()
+    else:
+        def e2e_loop(steps):
+            for s in range(steps):
+                e2e_step(s)
+
+    e2e_loop(3)
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
-    for s in range(a.steps):
-        e2e_step(s)
+    e2e_loop(a.steps)
     e2e_s = time.perf_counter() - t0
     if dist:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -532,6 +552,8 @@ def run_b200(a, rank, local_rank, world):
             "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
                     "api": "b200hnsw_search_batch (host pointers, pinned)" if sw == 1 else
+                           "PipelinedShardSearch.submit_host: pinned H2D, b200hnsw_search_batch_device, packed NCCL "
+                           "all_gather, merge kernel, pinned D2H; two batches in flight" if pipe is not None else
                            "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},
             "gpu_launches": a.steps * (1 if sw == 1 else 2),  # search kernel (+ merge kernel at N > 1)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

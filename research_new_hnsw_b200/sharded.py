@@ -144,6 +144,7 @@ class PipelinedShardSearch:
         self.index.searchKnnDevice(d_queries, self.nq, self.k, ef, pl, pd, 0, d_work, main.cuda_stream)
         searched = torch.cuda.Event()
         searched.record(main)
+        self.last_searched = searched
         self.side.wait_event(searched)
         with torch.cuda.stream(self.side):
             out_l, out_d = slot.exchange_and_merge(self.side.cuda_stream)
@@ -155,3 +156,38 @@ class PipelinedShardSearch:
     def drain(self):
         """make the caller's stream wait for every exchange in flight"""
         self.torch.cuda.current_stream().wait_stream(self.side)
+
+    def submit_host(self, h_queries, ef, h_labels, h_dists):
+        """Host-facing form of submit(): page-locked query batch in, page-locked result rows out.  The H2D copy, the
+        search, the exchange and the D2H copy of consecutive batches run on four streams ordered by events, so a
+        serving loop that keeps ``depth`` batches in flight overlaps all of them.  Returns the event after which
+        ``h_labels`` / ``h_dists`` hold the merged rows of this batch."""
+        torch = self.torch
+        if not hasattr(self, "_h2d"):
+            dev = self.slots[0].mine.device
+            self._h2d = torch.cuda.Stream(device=dev)
+            self._d2h = torch.cuda.Stream(device=dev)
+            self._dq = [torch.empty(tuple(h_queries.shape), dtype=torch.float32, device=dev) for _ in self.slots]
+            self._srch = [None] * len(self.slots)
+            self._down = [None] * len(self.slots)
+        j = self.i % len(self.slots)
+        main = torch.cuda.current_stream()
+        if self._srch[j] is not None:
+            self._h2d.wait_event(self._srch[j])      # the search that last read this query buffer
+        with torch.cuda.stream(self._h2d):
+            self._dq[j].copy_(h_queries, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(self._h2d)
+        main.wait_event(up)
+        if self._down[j] is not None:
+            self.side.wait_event(self._down[j])       # the D2H copy that last read this slot's merged rows
+        out_l, out_d, ev = self.submit(self._dq[j].data_ptr(), ef)
+        self._srch[j] = self.last_searched
+        self._d2h.wait_event(ev)
+        with torch.cuda.stream(self._d2h):
+            h_labels.copy_(out_l, non_blocking=True)
+            h_dists.copy_(out_d, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._d2h)
+        self._down[j] = done
+        return done

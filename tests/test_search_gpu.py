@@ -286,3 +286,21 @@ def test_pipelined_shard_search_single_rank(lib, graphs):
     torch.cuda.synchronize()
     for which, l, d in got:
         assert np.array_equal(l, want[which]["labels"]) and np.array_equal(d, want[which]["dists"])
+    # host-facing form: pinned queries in, pinned merged rows out, two batches in flight
+    hq = [torch.from_numpy(np.ascontiguousarray(h)).pin_memory() for h in halves]
+    hl = [torch.empty((len(halves[0]), 10), dtype=torch.int64).pin_memory() for _ in range(2)]
+    hd = [torch.empty((len(halves[0]), 10), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pend = [None, None]
+    for step in range(7):
+        j = step % 2
+        if pend[j] is not None:
+            pend[j][0].synchronize()
+            which = pend[j][1]
+            assert np.array_equal(hl[j].numpy().view(np.uint64), want[which]["labels"])
+            assert np.array_equal(hd[j].numpy(), want[which]["dists"])
+        which = (step // 2 + step) % 2
+        pend[j] = (pipe.submit_host(hq[which], 48, hl[j], hd[j]), which)
+    for j in range(2):
+        pend[j][0].synchronize()
+        assert np.array_equal(hl[j].numpy().view(np.uint64), want[pend[j][1]]["labels"])
+    torch.cuda.synchronize()
