@@ -381,9 +381,15 @@ def run_b200(a, rank, local_rank, world):
     if pipe is not None:
         # N > 1: batch i's all_gather + merge overlaps batch i+1's search kernel (side stream, event-ordered);
         # the timed region ends only after the last exchange has finished.
+        # The host keeps at most `inflight` batches enqueued (it waits for the exchange of batch s-inflight): with an
+        # unbounded queue the NCCL kernel of batch s is dispatched behind search kernels queued long before it.
+        inflight = int(os.environ.get("B200HNSW_BENCH_INFLIGHT", "2"))
+        evs = []
         t_submit = time.perf_counter()
         for s in range(a.steps):
-            pipe.submit(dbatches[s % len(dbatches)].data_ptr(), ef)
+            if inflight > 0 and s >= inflight:
+                evs[s - inflight].synchronize()
+            evs.append(pipe.submit(dbatches[s % len(dbatches)].data_ptr(), ef)[2])
         submit_ms = 1e3 * (time.perf_counter() - t_submit) / a.steps
         pipe.drain()
     else:

@@ -2,13 +2,15 @@
 # A/B of the N>1 exchange inside one gpurun call.  usage: probe_scale.sh N mode...   (modes: pipe serial ctas2 ll)
 N=${1:-2}; shift
 for mode in ${@:-pipe serial}; do
-  unset B200HNSW_BENCH_NO_PIPELINE NCCL_MAX_CTAS NCCL_MIN_CTAS NCCL_PROTO TORCH_NCCL_HIGH_PRIORITY B200HNSW_PIPE_DEPTH
+  unset B200HNSW_BENCH_INFLIGHT B200HNSW_BENCH_NO_PIPELINE NCCL_MAX_CTAS NCCL_MIN_CTAS NCCL_PROTO TORCH_NCCL_HIGH_PRIORITY B200HNSW_PIPE_DEPTH
   case $mode in
     d4) export B200HNSW_PIPE_DEPTH=4;;
     hp_d4) export B200HNSW_PIPE_DEPTH=4 TORCH_NCCL_HIGH_PRIORITY=1;;
     hp_d4_ctas2) export B200HNSW_PIPE_DEPTH=4 TORCH_NCCL_HIGH_PRIORITY=1 NCCL_MAX_CTAS=2 NCCL_MIN_CTAS=1;;
     hp) export TORCH_NCCL_HIGH_PRIORITY=1;;
     serial) export B200HNSW_BENCH_NO_PIPELINE=1;;
+    unbounded) export B200HNSW_BENCH_INFLIGHT=0;;
+    inflight3) export B200HNSW_BENCH_INFLIGHT=3;;
     ctas2) export NCCL_MAX_CTAS=2 NCCL_MIN_CTAS=1;;
     ll) export NCCL_PROTO=LL;;
   esac
