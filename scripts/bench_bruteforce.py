@@ -15,6 +15,51 @@ ap.add_argument("--nq", type=int, default=10_000); ap.add_argument("--k", type=i
 ap.add_argument("--steps", type=int, default=10); ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 import torch
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+if WORLD > 1:
+    # SURVEY.md 8(e), brute force: rows sharded across GPUs (strong scaling: the SAME 1M rows, 1/N per GPU), every GPU
+    # scans its rows for the whole query batch, one packed all_gather of the per-shard top-k + GPU merge.
+    import torch.distributed as dist
+    from research_new_hnsw_b200.sharded import PackedShardExchange, shard_range
+    rank, lrank = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lrank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+    dev = torch.device("cuda", lrank)
+    X = lowrank_data(a.n, a.dim, seed=1, latent=64, noise=0.1, normalize=True)
+    Qs = [lowrank_data(a.nq, a.dim, seed=2 + 7 * b, latent=64, noise=0.1, normalize=True) for b in range(2)]
+    lo, hi = shard_range(a.n, rank, WORLD)
+    g = pkg.BruteforceSearch(pkg.InnerProductSpace(a.dim), hi - lo, device=lrank)
+    g.addPoints(X[lo:hi], np.arange(lo, hi, dtype=np.uint64))
+    dQ = [torch.from_numpy(q).to(dev) for q in Qs]
+    ex = PackedShardExchange(a.nq, a.k, dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    def step(s):
+        pl, pd = ex.local_ptrs()
+        g.searchKnnDevice(dQ[s % 2].data_ptr(), a.nq, a.k, pl, pd, 0, stream)
+        return ex.exchange_and_merge(stream)
+    for s in range(a.warmup): step(s)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(a.steps): ol, od = step(s)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / a.steps
+    if rank == 0:
+        full = pkg.BruteforceSearch(pkg.InnerProductSpace(a.dim), a.n, device=lrank)
+        full.addPoints(X)
+        ref = full.searchKnnBatch(Qs[(a.steps - 1) % 2][:256], a.k)
+        same = bool(np.array_equal(ref["labels"], ol[:256].cpu().numpy().view(np.uint64))
+                    and np.array_equal(ref["dists"], od[:256].cpu().numpy()))
+        print(json.dumps({"metric": "BruteforceSearch exact k=%d QPS, %dx%d inner product, rows sharded over %d GPUs"
+                          % (a.k, a.n, a.dim, WORLD), "value": a.nq / (ms * 1e-3), "unit": "queries/s", "n_gpus": WORLD,
+                          "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "strong", "data": "synthetic",
+                          "config": {"workload": "C4 rows split %d ways, %d queries per batch, one packed all_gather + merge"
+                                     % (WORLD, a.nq), "merged_equals_single_gpu_256_queries": same}}))
+    dist.barrier()
+    sys.exit(0)
 X = lowrank_data(a.n, a.dim, seed=1, latent=64, noise=0.1, normalize=True)
 Qs = [lowrank_data(a.nq, a.dim, seed=2 + 7 * b, latent=64, noise=0.1, normalize=True) for b in range(2)]
 g = pkg.BruteforceSearch(pkg.InnerProductSpace(a.dim), a.n)
