@@ -7,7 +7,7 @@
 //
 //   * persistent grid, one CTA per SM, CTA b walks row tiles b, b+grid, ... of 64 rows;
 //   * a producer warp moves 64 rows x 512 B per stage with 16-byte cp.async copies (one warp instruction = 512
-//     contiguous bytes of one row, completion on an mbarrier via cp.async.mbarrier.arrive) into a 4-stage ring laid out
+//     contiguous bytes of one row, completion on an mbarrier via cp.async.mbarrier.arrive) into a ring of 32 KB stages laid out
 //     like a 128-byte-swizzled TMA tile: the eight 16 B chunks of a 128 B row segment are XOR-ed with the row number,
 //     so lane = row reads are conflict-free without padding.  Measured alternatives on 1M x 768, one query: one 512 B
 //     1-D bulk copy (cp.async.bulk) per row 4.5 ms (64 small TMA operations per stage); four 64-row x 128 B swizzled
@@ -29,15 +29,15 @@ namespace b200 {
 
 constexpr int kStRows = 64;                     // rows per tile
 constexpr int kStKC4 = 32;                      // 128-bit chunks per row per stage (512 B)
-constexpr int kStStages = 4;
+constexpr int kStMaxStages = 8;                 // ring depth is chosen at launch: as many 32 KB stages as fit (<= 6 in 227 KB)
 constexpr int kStBoxBytes = kStRows * 128;      // one TMA box: 64 rows x 32 floats
 constexpr int kStStageBytes = kStRows * kStKC4 * 16;
 
 struct StreamSmem {
     uint32_t off_stage, off_q, off_topl, off_topd, off_ql, off_qd, off_meta, total;
-    __host__ __device__ StreamSmem(uint32_t nqt, uint32_t d4, uint32_t k) {
+    __host__ __device__ StreamSmem(uint32_t nqt, uint32_t d4, uint32_t k, uint32_t stages) {
         uint32_t o = 0;
-        off_stage = o; o += kStStages * kStStageBytes + 1024;  // + slack: the ring is aligned to 1024 B at run time
+        off_stage = o; o += stages * kStStageBytes + 1024;  // + slack: the ring is aligned to 1024 B at run time
         off_q = o;     o += nqt * d4 * 16;
         off_topl = o;  o += nqt * k * 8;
         off_ql = o;    o += nqt * kStRows * 8;
@@ -93,11 +93,11 @@ template <int METRIC, int QS, int P>
 __global__ void __launch_bounds__(64 * QS + 32, 1)
     bf_stream_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels, uint32_t n, uint32_t d4,
                      uint32_t lane_chunks, uint32_t dim, const float *__restrict__ Q, uint32_t nq, uint32_t k,
-                     float *__restrict__ part_d, uint64_t *__restrict__ part_l) {
+                     uint32_t stages, float *__restrict__ part_d, uint64_t *__restrict__ part_l) {
     constexpr int NQT = QS * P, NCOMP = 64 * QS, NCW = NCOMP / 32;
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ __align__(8) uint64_t full[kStStages], empty[kStStages];
-    const StreamSmem L(NQT, d4, k);
+    __shared__ __align__(8) uint64_t full[kStMaxStages], empty[kStMaxStages];
+    const StreamSmem L(NQT, d4, k, stages);
     unsigned char *ring = smem + ((1024u - (st_smem_u32(smem) & 1023u)) & 1023u);  // 128-byte swizzle needs 1024 B alignment
     float4 *sQ = (float4 *)(smem + L.off_q);
     uint64_t *topl = (uint64_t *)(smem + L.off_topl);
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
     const uint32_t nkc = (d4 + kStKC4 - 1) / kStKC4;
 
     if (tid == 0) {
-        for (int s = 0; s < kStStages; s++) {
+        for (uint32_t s = 0; s < stages; s++) {
             st_mbar_init(full + s, 32);  // one deferred arrival per producer lane
             st_mbar_init(empty + s, NCW);
         }
@@ -136,12 +136,11 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
 
     if (warp == NCW) {
         // ---- producer warp: lane = 16-byte chunk of the stage's 512-byte row segment
-        uint32_t it = 0;
+        uint32_t s = 0, ph = 0;
         const uint32_t slot = (uint32_t)(lane >> 3) * kStBoxBytes;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const uint32_t rows = min((uint32_t)kStRows, n - tile * kStRows);
-            for (uint32_t kc = 0; kc < nkc; kc++, it++) {
-                const uint32_t s = it % kStStages, ph = (it / kStStages) & 1;
+            for (uint32_t kc = 0; kc < nkc; kc++, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0)) {
                 const uint32_t ci = kc * kStKC4 + lane;
                 st_mbar_wait(empty + s, ph ^ 1);
                 if (ci < d4) {  // rows / chunks past the end are never read by the compute threads
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
     uint32_t xo[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) xo[j] = ((uint32_t)j ^ sw) << 4;
-    uint32_t it = 0;
+    uint32_t s = 0, ph = 0;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         float acc[P][4], tail[P];
 #pragma unroll
@@ -172,8 +171,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
 #pragma unroll
             for (int l = 0; l < 4; l++) acc[p][l] = 0.f;
         }
-        for (uint32_t kc = 0; kc < nkc; kc++, it++) {
-            const uint32_t s = it % kStStages, ph = (it / kStStages) & 1;
+        for (uint32_t kc = 0; kc < nkc; kc++, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0)) {
             const uint32_t base = kc * kStKC4;
             const uint32_t c4 = min((uint32_t)kStKC4, d4 - base);
             const uint32_t nl = base < lane_chunks ? min(c4, lane_chunks - base) : 0u;
@@ -312,12 +310,12 @@ __global__ void bf_stream_counts_kernel(uint32_t *counts, uint32_t nq, uint32_t 
 template <int METRIC, int QS, int P>
 static cudaError_t stream_launch(dim3 grid, uint32_t smem_bytes, cudaStream_t st, const float4 *X, const uint64_t *labels,
                                  uint32_t n, uint32_t d4, uint32_t lane_chunks, uint32_t dim, const float *Q, uint32_t nq,
-                                 uint32_t k, float *pd, uint64_t *pl) {
+                                 uint32_t k, uint32_t stages, float *pd, uint64_t *pl) {
     cudaError_t e = cudaFuncSetAttribute(bf_stream_kernel<METRIC, QS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem_bytes);
     if (e != cudaSuccess) return e;
     bf_stream_kernel<METRIC, QS, P><<<grid, 64 * QS + 32, smem_bytes, st>>>(X, labels, n, d4, lane_chunks, dim, Q, nq, k,
-                                                                            pd, pl);
+                                                                            stages, pd, pl);
     return cudaGetLastError();
 }
 
@@ -333,21 +331,26 @@ int BruteIndex::search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *d
         B200_CUDA_OK(cudaDeviceGetAttribute(&smem_optin[di], cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         B200_CUDA_OK(cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, device));
     }
-    // static shared memory of the kernel: 2 * kStStages mbarriers
-    const size_t budget = (size_t)smem_optin[di] - 2 * kStStages * 8 - 64;
+    // static shared memory of the kernel: 2 * kStMaxStages mbarriers
+    const size_t budget = (size_t)smem_optin[di] - 2 * kStMaxStages * 8 - 64;
     // queries per pass: the largest of {16, 8, 4, 2, 1} that is useful and fits.  A row chunk read from shared memory
     // serves the P queries of its thread, so P grows before the number of query slots does (with 8 slots x 1 query
-    // the rows were re-read 8 times and shared-memory bandwidth, not HBM, set the pace).
+    // the rows were re-read 8 times and shared-memory bandwidth, not HBM, set the pace).  The ring takes what is left
+    // (measured at one query: 2 / 4 / 6 stages = 0.895 / 0.772 / 0.769 ms, so depth beyond 4 is not the limiter).
     static const int cfg_qs[5] = {4, 4, 4, 2, 1}, cfg_p[5] = {4, 2, 1, 1, 1};
+    const char *es = getenv("B200HNSW_BF_STAGES");
+    const uint32_t max_stages = es ? (uint32_t)std::min(6, std::max(2, atoi(es))) : 6u;
     int pick = -1;
-    for (int c = 0; c < 5; c++) {
+    uint32_t stages = 0;
+    for (int c = 0; c < 5 && pick < 0; c++) {
         const size_t nqt = (size_t)cfg_qs[c] * cfg_p[c];
         if (c + 1 < 5 && nqt / 2 >= nq) continue;  // a smaller pass already covers nq
-        if (StreamSmem((uint32_t)nqt, (uint32_t)d4, (uint32_t)k).total <= budget) { pick = c; break; }
+        for (uint32_t t = max_stages; t >= 3 || (t >= 2 && es); t--)
+            if (StreamSmem((uint32_t)nqt, (uint32_t)d4, (uint32_t)k, t).total <= budget) { pick = c; stages = t; break; }
     }
     if (pick < 0) return 1;
     const size_t nqt = (size_t)cfg_qs[pick] * cfg_p[pick];
-    const uint32_t smem_bytes = StreamSmem((uint32_t)nqt, (uint32_t)d4, (uint32_t)k).total;
+    const uint32_t smem_bytes = StreamSmem((uint32_t)nqt, (uint32_t)d4, (uint32_t)k, stages).total;
     const size_t ntiles = (n + kStRows - 1) / kStRows;
     const size_t slices = std::min<size_t>(ntiles, (size_t)sm_count[di]);
     const size_t passes = (nq + nqt - 1) / nqt;
@@ -368,10 +371,10 @@ int BruteIndex::search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *d
 #define B200_STREAM_CASE(QS_, P_)                                                                                       \
     e = m == 0 ? stream_launch<0, QS_, P_>(grid, smem_bytes, st, dX, dLabels, (uint32_t)n, (uint32_t)d4,                \
                                            (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_, (uint32_t)nq, (uint32_t)k,  \
-                                           dPartD, dPartL)                                                              \
+                                           stages, dPartD, dPartL)                                                              \
                : stream_launch<1, QS_, P_>(grid, smem_bytes, st, dX, dLabels, (uint32_t)n, (uint32_t)d4,                \
                                            (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_, (uint32_t)nq, (uint32_t)k,  \
-                                           dPartD, dPartL)
+                                           stages, dPartD, dPartL)
     switch (pick) {
         case 0: B200_STREAM_CASE(4, 4); break;
         case 1: B200_STREAM_CASE(4, 2); break;
