@@ -23,6 +23,8 @@
 #include <cstring>
 
 #include "bruteforce.cuh"
+#include "bf_topk.cuh"
+#include "mbarrier.cuh"
 #include "merge_launch.cuh"
 
 namespace b200 {
@@ -48,37 +50,6 @@ struct StreamSmem {
     }
 };
 
-__device__ __forceinline__ uint32_t st_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void st_mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void st_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void st_mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void st_mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(st_smem_u32(bar)), "r"(parity) : "memory");
-}
-// 16-byte asynchronous copy global -> shared (LDGSTS), L2 only; completion is attached to an mbarrier below
-__device__ __forceinline__ void st_cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st_smem_u32(dst)), "l"(src) : "memory");
-}
-// the mbarrier receives one arrival from this thread once all its earlier cp.async copies have landed
-__device__ __forceinline__ void st_cp_async_arrive(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(st_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool st_pair_less(float d1, uint64_t l1, float d2, uint64_t l2) {
-    return d1 < d2 || (d1 == d2 && l1 < l2);
-}
-
 template <int METRIC>
 __device__ __forceinline__ float st_term(float q, float x) {
     if (METRIC == 0) {
@@ -98,7 +69,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[kStMaxStages], empty[kStMaxStages];
     const StreamSmem L(NQT, d4, k, stages);
-    unsigned char *ring = smem + ((1024u - (st_smem_u32(smem) & 1023u)) & 1023u);  // 128-byte swizzle needs 1024 B alignment
+    unsigned char *ring = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);  // 128-byte swizzle needs 1024 B alignment
     float4 *sQ = (float4 *)(smem + L.off_q);
     uint64_t *topl = (uint64_t *)(smem + L.off_topl);
     float *topd = (float *)(smem + L.off_topd);
@@ -113,10 +84,10 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
 
     if (tid == 0) {
         for (uint32_t s = 0; s < stages; s++) {
-            st_mbar_init(full + s, 32);  // one deferred arrival per producer lane
-            st_mbar_init(empty + s, NCW);
+            mbar_init(full + s, 32);  // one deferred arrival per producer lane
+            mbar_init(empty + s, NCW);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     {   // queries of this pass, zero-padded to d4 chunks (rows of Q are only 4-byte aligned in general)
         float *sQf = (float *)sQ;
@@ -142,15 +113,15 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
             const uint32_t rows = min((uint32_t)kStRows, n - tile * kStRows);
             for (uint32_t kc = 0; kc < nkc; kc++, s = (s + 1 == stages ? 0 : s + 1), ph ^= (s == 0)) {
                 const uint32_t ci = kc * kStKC4 + lane;
-                st_mbar_wait(empty + s, ph ^ 1);
+                mbar_wait(empty + s, ph ^ 1);
                 if (ci < d4) {  // rows / chunks past the end are never read by the compute threads
                     unsigned char *dst = ring + s * kStStageBytes + slot;
                     const float4 *src = X + (size_t)tile * kStRows * d4 + ci;
 #pragma unroll 8
                     for (uint32_t r = 0; r < rows; r++)
-                        st_cp_async16(dst + r * 128 + (((uint32_t)(lane & 7) ^ (r & 7)) << 4), src + (size_t)r * d4);
+                        cp_async16(dst + r * 128 + (((uint32_t)(lane & 7) ^ (r & 7)) << 4), src + (size_t)r * d4);
                 }
-                st_cp_async_arrive(full + s);
+                cp_async_arrive(full + s);
             }
         }
         return;
@@ -175,7 +146,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
             const uint32_t base = kc * kStKC4;
             const uint32_t c4 = min((uint32_t)kStKC4, d4 - base);
             const uint32_t nl = base < lane_chunks ? min(c4, lane_chunks - base) : 0u;
-            st_mbar_wait(full + s, ph);
+            mbar_wait(full + s, ph);
             // chunk c of row r lives in box c/8 at 16-byte slot (c%8) ^ (r%8) of the row's 128-byte segment
             const unsigned char *sx = ring + s * kStStageBytes + r * 128;
             const float4 *sq = sQ + (size_t)(qs * P) * d4 + base;
@@ -221,7 +192,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
                 }
             }
             __syncwarp();
-            if (lane == 0) st_mbar_arrive(empty + s);
+            if (lane == 0) mbar_arrive(empty + s);
         }
         // distances of this row -> candidate queues
         const uint32_t g = tile * kStRows + r;
@@ -247,36 +218,8 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
             int cnt = meta[qq * 4 + 0], wpos = meta[qq * 4 + 1];
             float wd = cnt == (int)k ? td[wpos] : 0.f;
             uint64_t wl = cnt == (int)k ? tl[wpos] : 0;
-            for (int e = 0; e < m; e++) {
-                const float cd = qd[qq * kStRows + e];
-                const uint64_t cl = ql[qq * kStRows + e];
-                if (cnt < (int)k) {
-                    if (lane == 0) { td[cnt] = cd; tl[cnt] = cl; }
-                    cnt++;
-                    if (cnt < (int)k) continue;
-                } else {
-                    if (!st_pair_less(cd, cl, wd, wl)) continue;
-                    if (lane == 0) { td[wpos] = cd; tl[wpos] = cl; }
-                }
-                __syncwarp();
-                float bd = -3.402823466e+38f;  // recompute the worst (largest (dist,label)) entry
-                uint64_t bl = 0;
-                int bp = -1;
-                for (int i = lane; i < (int)k; i += 32) {
-                    const float ed = td[i];
-                    const uint64_t el = tl[i];
-                    if (bp < 0 || st_pair_less(bd, bl, ed, el)) { bd = ed; bl = el; bp = i; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-                    const uint64_t ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-                    if (op >= 0 && (bp < 0 || st_pair_less(bd, bl, od, ol))) { bd = od; bl = ol; bp = op; }
-                }
-                wd = bd; wl = bl; wpos = bp;
-                __syncwarp();
-            }
+            for (int e = 0; e < m; e++)
+                topk_insert(td, tl, (int)k, cnt, wpos, wd, wl, qd[qq * kStRows + e], ql[qq * kStRows + e], lane);
             if (lane == 0) {
                 meta[qq * 4 + 0] = cnt;
                 meta[qq * 4 + 1] = wpos;

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "bruteforce.cuh"
+#include "bf_topk.cuh"
 #include "merge_launch.cuh"
 
 namespace b200 {
@@ -28,10 +29,6 @@ struct BfSmem {
         total = o;
     }
 };
-
-__device__ __forceinline__ bool pair_less(float d1, uint64_t l1, float d2, uint64_t l2) {
-    return d1 < d2 || (d1 == d2 && l1 < l2);
-}
 
 // One CTA: 64 queries x one slice of rows.  Distances are accumulated exactly like the reference's SSE kernels:
 // lane_chunks 128-bit chunks go to four per-lane accumulators, the remaining (< 16) elements to a sequential
@@ -172,32 +169,7 @@ __global__ void __launch_bounds__(kBfThreads) bf_scan_kernel(const float4 *__res
                     m &= m - 1;
                     const float cd = __shfl_sync(0xffffffffu, d, src);
                     const uint64_t cl = __shfl_sync(0xffffffffu, lab, src);
-                    if (cnt < (int)k) {
-                        if (lane == 0) { td[cnt] = cd; tl[cnt] = cl; }
-                        cnt++;
-                        if (cnt < (int)k) continue;
-                    } else {
-                        if (!pair_less(cd, cl, wd, wl)) continue;
-                        if (lane == 0) { td[wpos] = cd; tl[wpos] = cl; }
-                    }
-                    __syncwarp();
-                    // recompute the worst (largest (dist,label)) entry
-                    float bd = -3.402823466e+38f;
-                    uint64_t bl = 0;
-                    int bp = -1;
-                    for (int e = lane; e < (int)k; e += 32) {
-                        const float ed = td[e];
-                        const uint64_t el = tl[e];
-                        if (bp < 0 || pair_less(bd, bl, ed, el)) { bd = ed; bl = el; bp = e; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-                        const uint64_t ol = __shfl_xor_sync(0xffffffffu, bl, o);
-                        const int op = __shfl_xor_sync(0xffffffffu, bp, o);
-                        if (op >= 0 && (bp < 0 || pair_less(bd, bl, od, ol))) { bd = od; bl = ol; bp = op; }
-                    }
-                    wd = bd; wl = bl; wpos = bp;
+                    topk_insert(td, tl, (int)k, cnt, wpos, wd, wl, cd, cl, lane);
                 }
             }
             if (lane == 0) { meta[qq * 2] = cnt; meta[qq * 2 + 1] = wpos; }
