@@ -105,7 +105,10 @@ int b200hnsw_set_ef(b200hnsw_index *h, size_t ef);
 /* addPoint(const void*, labeltype), hnswalg.h:954-964 -> 1153-1267, batched: n rows of dim floats and n labels.
  * Levels, element count, entry point and max level are assigned immediately in row order with the reference's
  * level generator (hnswalg.h:207-211,1187-1198,1255-1265); graph linking may be deferred until b200hnsw_flush
- * (or any call that reads the graph).  labels == NULL means labels cur_element_count .. +n-1. */
+ * (or any call that reads the graph).  labels == NULL means labels cur_element_count .. +n-1.
+ * A label that already exists is UPDATED (hnswalg.h:1157-1174 -> updatePoint, :995-1139): new vector, delete mark
+ * cleared, and the point is re-linked on the GPU (repairConnectionsForUpdate, :1075-1139; the re-pruning of its old
+ * neighbours, :1009-1069, is not performed). */
 int b200hnsw_add_batch(b200hnsw_index *h, const float *X, const uint64_t *labels, size_t n);
 /* Links every staged point into the graph on the GPU and refreshes the host mirror. */
 int b200hnsw_flush(b200hnsw_index *h);

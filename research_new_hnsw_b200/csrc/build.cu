@@ -43,6 +43,8 @@ struct BuildArgs {
     uint64_t *incoming;        // [cap + up_lists_cap][kCapIn]
     uint32_t *aff_node, *aff_level, *aff_count;
     unsigned long long *work;  // [4] D, H0, Hup, resets (atomicAdd)
+    const uint32_t *batch_ids;  // update mode: ids of the (already linked) points of this batch; else first + b
+    uint32_t update;            // 1: re-link existing points (repairConnectionsForUpdate, hnswalg.h:1075-1139)
     uint32_t cap, first, batch, lists;
     uint32_t entry;
     int32_t maxlevel;
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
 
     const int tid = threadIdx.x;
     const int sub = tid % LPV, grp = tid / LPV;
-    const uint32_t pid = p.first + blockIdx.x;
+    const uint32_t pid = p.batch_ids ? p.batch_ids[blockIdx.x] : p.first + blockIdx.x;
     const uint32_t HS = 1u << p.hash_bits;
     const int plevel = p.plevel[pid];
 
@@ -180,10 +182,37 @@ __global__ void __launch_bounds__(kTeam) build_link_kernel(const BuildArgs p) {
     const int tid = threadIdx.x;
     const uint32_t slot = blockIdx.x;
     const uint32_t pid = p.list_point[slot], level = p.list_level[slot];
-    const int n = (int)p.cand_cnt[slot];
+    int n = (int)p.cand_cnt[slot];
+    uint64_t *cand = p.cand + (size_t)slot * p.efc;
+    if (p.update) {
+        // the point is already in the graph, so its own search finds it: drop it from the candidates
+        // (filteredTopCandidates, hnswalg.h:1117-1123) by closing the gap in the sorted list
+        __shared__ int s_self;
+        if (tid == 0) s_self = n;
+        __syncthreads();
+        for (int j = tid; j < n; j += kTeam)
+            if (((uint32_t)cand[j] & kIdMask) == pid) s_self = j;
+        __syncthreads();
+        const int self = s_self;
+        if (self < n) {
+            for (int base = self; base < n - 1; base += kTeam) {
+                const int j = base + tid;
+                const uint64_t v = j < n - 1 ? cand[j + 1] : 0;
+                __syncthreads();
+                if (j < n - 1) cand[j] = v;
+                __syncthreads();
+            }
+            n--;
+        }
+        if (n == 0) return;  // nothing but the point itself on this level: its links stay (hnswalg.h:1127)
+    }
     uint32_t evals = 0;
-    const int ns = heuristic_prune<LPV, CPL, METRIC>(g, p.cand + (size_t)slot * p.efc, n, (int)p.M, sel, ids, dist, evals);
+    const int ns = heuristic_prune<LPV, CPL, METRIC>(g, cand, n, (int)p.M, sel, ids, dist, evals);
     uint32_t *mine = list_ptr(p, pid, level);
+    if (p.update) {  // the old forward list is replaced, not extended
+        const int Mcur = (int)(level ? p.maxM : p.maxM0);
+        for (int j = ns + tid; j < Mcur; j += kTeam) mine[j] = kEmpty;
+    }
     for (int j = tid; j < ns; j += kTeam) {
         const uint32_t r = ids[j];
         mine[j] = r;
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p,
     if (blockIdx.x >= n_aff) return;
     const uint32_t node = p.aff_node[blockIdx.x], level = p.aff_level[blockIdx.x];
     const uint32_t lid = list_id(p, node, level);
-    const int t = (int)min(p.incnt[lid], kCapIn);
+    int t = (int)min(p.incnt[lid], kCapIn);
     const int Mcur = (int)(level ? p.maxM : p.maxM0);
     uint32_t *lst = list_ptr(p, node, level);
     int deg = 0;
@@ -229,6 +258,24 @@ __global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p,
     for (int j = tid; j < t; j += kTeam) raw[deg + j] = p.incoming[(size_t)lid * kCapIn + j];
     __syncthreads();
     if (tid == 0) p.incnt[lid] = 0;  // ready for the next batch
+    if (p.update) {
+        // a re-linked point may already be a neighbour of this node (is_cur_c_present, hnswalg.h:566-580): keep the
+        // existing edge, drop the incoming duplicate
+        __shared__ int s_keep;
+        if (tid == 0) {
+            int keep = 0;
+            for (int j = 0; j < t; j++) {
+                const uint64_t key = raw[deg + j];
+                bool present = false;
+                for (int i = 0; i < deg; i++) present |= ids[i] == (uint32_t)key;
+                if (!present) raw[deg + keep++] = key;
+            }
+            s_keep = keep;
+        }
+        __syncthreads();
+        t = s_keep;
+        if (t == 0) return;
+    }
     if (deg + t <= Mcur) {
         // room for all (hnswalg.h:586-588); ordered by new id so the list does not depend on atomic arrival order
         for (int j = tid; j < t; j += kTeam) {
@@ -304,15 +351,37 @@ static int run_batch_metric(const BuildArgs &a, size_t s1, size_t s2, uint32_t *
 
 // ---- host side ---------------------------------------------------------------------------------------------
 
+static size_t env_size(const char *name, size_t dflt) {
+    if (const char *e = getenv(name)) {
+        const long long v = atoll(e);
+        if (v > 0) return (size_t)v;
+    }
+    return dflt;
+}
+
 // addPoint staging (hnswalg.h:1153-1211,1255-1265): everything that does not need a distance.
 int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n) {
     std::lock_guard<std::mutex> g(mu);
     HostImage &m = host;
+    std::vector<uint32_t> updates;
     for (size_t i = 0; i < n; i++) {
         const uint64_t lab = labels ? labels[i] : (uint64_t)m.cur;
-        if (m.label_lookup.count(lab)) {
-            set_error("addPoint with an existing label (updatePoint, hnswalg.h:995) is not supported by the GPU engine");
-            return B200HNSW_E_UNSUPPORTED;
+        auto known = m.label_lookup.find(lab);
+        if (known != m.label_lookup.end()) {
+            // existing label: update instead of insert (hnswalg.h:1157-1174)
+            const uint32_t c = known->second;
+            if (m.deleted(c)) {
+                if (prm.allow_replace_deleted) {
+                    set_error("Can't use addPoint to update deleted elements if replacement of deleted elements is enabled.");
+                    return B200HNSW_E_STATE;
+                }
+                *((unsigned char *)m.rec(c) + 2) &= (unsigned char)~1;  // unmarkDeletedInternal
+                m.num_deleted--;
+                flags_dirty = true;
+            }
+            memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
+            if (c < linked) updates.push_back(c);  // a staged point is simply linked with its new vector later
+            continue;
         }
         if (m.cur >= m.max_elements) {
             set_error("The number of elements exceeds the specified limit");
@@ -334,7 +403,71 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n) {
             m.maxlevel = level;
         }
     }
-    return 0;
+    return updates.empty() ? 0 : relink_points(std::move(updates));
+}
+
+// updatePoint (hnswalg.h:995-1139) for points that are already part of the device graph, batched.  The new vector is
+// uploaded, then repairConnectionsForUpdate runs on the GPU with the construction kernels in update mode: search from the
+// entry point, the point itself dropped from its candidates, heuristic selection, forward list REPLACED, reverse edges
+// added unless already present (mutuallyConnectNewElement with isUpdate, :485-639).  The first phase of the reference --
+// re-pruning every old neighbour over the 1-hop/2-hop neighbourhood (:1009-1069) -- is NOT performed: old neighbours keep
+// their edge to the moved point.
+int HnswIndex::relink_points(std::vector<uint32_t> ids) {
+    HostImage &m = host;
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    {   // new vectors -> padded device rows
+        std::vector<float> row(dev.d4 * 4, 0.f);
+        for (uint32_t id : ids) {
+            memcpy(row.data(), m.rec(id) + m.off_data, m.dim * 4);
+            B200_CUDA_OK(cudaMemcpy((float *)dev.vec + (size_t)id * dev.d4 * 4, row.data(), dev.d4 * 16, cudaMemcpyHostToDevice));
+            const int rc16 = sync_bf16(id, 1);
+            if (rc16) return rc16;
+        }
+    }
+    if (linked <= 1) return 0;  // a single element has nothing to connect to (hnswalg.h:1001-1003)
+    const size_t build_ratio = env_size("B200HNSW_BUILD_RATIO", 32);
+    const size_t max_batch = env_size("B200HNSW_BUILD_BATCH", 16384);
+    if (!bld.plevel) B200_CUDA_OK(cudaMalloc(&bld.plevel, std::max<size_t>(dev.cap, 1) * 4));
+    B200_CUDA_OK(cudaMemcpy(bld.plevel, m.levels.data(), linked * 4, cudaMemcpyHostToDevice));
+    BuildArgs a{};
+    size_t max_lists = 0, smem_search = 0, smem_link = 0;
+    int rc = prepare_build(&a, max_batch, &max_lists, &smem_search, &smem_link);
+    if (rc) return rc;
+    if (!bld.batch_ids) B200_CUDA_OK(cudaMalloc(&bld.batch_ids, max_batch * 4));
+    std::vector<uint32_t> off, lp, ll;
+    uint32_t h_aff = 0;
+    uint64_t launches = 0;
+    for (size_t b0 = 0; b0 < ids.size() && rc == 0;) {
+        size_t B = std::max<size_t>(1, std::min(max_batch, linked / build_ratio));
+        B = std::min(B, ids.size() - b0);
+        off.clear(); lp.clear(); ll.clear();
+        size_t used = 0;
+        for (; used < B; used++) {
+            const uint32_t id = ids[b0 + used];
+            const int top = std::min(m.levels[id], dev_maxlevel);
+            if (lp.size() + (size_t)top + 1 > max_lists) break;
+            off.push_back((uint32_t)lp.size());
+            for (int l = 0; l <= top; l++) { lp.push_back(id); ll.push_back((uint32_t)l); }
+        }
+        B = used;
+        B200_CUDA_OK(cudaMemcpyAsync(bld.batch_ids, ids.data() + b0, B * 4, cudaMemcpyHostToDevice, stream));
+        B200_CUDA_OK(cudaMemcpyAsync(bld.list_off, off.data(), B * 4, cudaMemcpyHostToDevice, stream));
+        B200_CUDA_OK(cudaMemcpyAsync(bld.list_point, lp.data(), lp.size() * 4, cudaMemcpyHostToDevice, stream));
+        B200_CUDA_OK(cudaMemcpyAsync(bld.list_level, ll.data(), ll.size() * 4, cudaMemcpyHostToDevice, stream));
+        a.first = 0; a.batch = (uint32_t)B; a.lists = (uint32_t)lp.size();
+        a.entry = dev_entry; a.maxlevel = dev_maxlevel;
+        a.batch_ids = bld.batch_ids; a.update = 1;
+        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0>(a, smem_search, smem_link, &h_aff, stream)
+                                       : run_batch_metric<1>(a, smem_search, smem_link, &h_aff, stream);
+        launches += 3;
+        b0 += B;
+    }
+    if (rc == 0) B200_CUDA_OK(cudaStreamSynchronize(stream));
+    stats.kernel_launches += launches;
+    mirror_dirty = true;
+    return rc;
 }
 
 // Device graph -> reference-layout host mirror (needed by saveIndex and get_linklist*).
@@ -378,13 +511,65 @@ int HnswIndex::sync_host_mirror() {
     return 0;
 }
 
-static size_t env_size(const char *name, size_t dflt) {
-    if (const char *e = getenv(name)) {
-        const long long v = atoll(e);
-        if (v > 0) return (size_t)v;
+// Scratch of the build kernels (sized for batches of max_batch points) and the kernel arguments that do not depend on
+// the batch; shared by flush() (new points) and relink_points() (updatePoint).
+int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out, size_t *smem_search, size_t *smem_link) {
+    HostImage &m = host;
+    const size_t nl = dev.cap + dev.up_lists_cap;
+    if (!bld.plevel) B200_CUDA_OK(cudaMalloc(&bld.plevel, std::max<size_t>(dev.cap, 1) * 4));
+    if (!bld.incnt) {
+        B200_CUDA_OK(cudaMalloc(&bld.incnt, nl * 4));
+        B200_CUDA_OK(cudaMemset(bld.incnt, 0, nl * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.incoming, nl * kCapIn * 8));
     }
-    return dflt;
+    const size_t max_lists = max_batch + max_batch / 2 + 64;  // level-0 list per point + the rare upper lists
+    *max_lists_out = max_lists;
+    if (!bld.cand || bld.cand_efc != m.efc) {
+        cudaFree(bld.cand); cudaFree(bld.cand_cnt); cudaFree(bld.list_off); cudaFree(bld.list_point);
+        cudaFree(bld.list_level); cudaFree(bld.aff_node); cudaFree(bld.aff_level); cudaFree(bld.aff_count);
+        cudaFree(bld.work);
+        B200_CUDA_OK(cudaMalloc(&bld.cand, max_lists * m.efc * 8));
+        B200_CUDA_OK(cudaMalloc(&bld.cand_cnt, max_lists * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.list_off, max_batch * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.list_point, max_lists * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.list_level, max_lists * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.aff_node, max_lists * m.M * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.aff_level, max_lists * m.M * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.aff_count, 4));
+        B200_CUDA_OK(cudaMemset(bld.aff_count, 0, 4));
+        B200_CUDA_OK(cudaMalloc(&bld.work, 32));
+        bld.cand_efc = m.efc;
+    }
+    B200_CUDA_OK(cudaMemset(bld.work, 0, 32));
+
+    const size_t list_cap = std::max(m.maxM, m.maxM0);
+    BuildArgs &a = *(BuildArgs *)args;
+    a = BuildArgs{};
+    a.vec = dev.vec; a.links0 = dev.links0; a.up_base = dev.up_base; a.links_up = dev.links_up;
+    a.plevel = bld.plevel; a.cand = bld.cand; a.cand_cnt = bld.cand_cnt; a.list_off = bld.list_off;
+    a.list_point = bld.list_point; a.list_level = bld.list_level; a.incnt = bld.incnt; a.incoming = bld.incoming;
+    a.aff_node = bld.aff_node; a.aff_level = bld.aff_level; a.aff_count = bld.aff_count; a.work = bld.work;
+    a.cap = (uint32_t)dev.cap; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)m.maxM; a.maxM0 = (uint32_t)m.maxM0;
+    a.M = (uint32_t)m.M; a.efc = (uint32_t)m.efc;
+    // construction searches evaluate ~40 * efc nodes; a table of ~32 * efc slots is rebuilt about once in four searches
+    // and lets twice as many CTAs share an SM as the no-rebuild size (measured: -30 % build time, same graph)
+    {
+        size_t want = std::min<size_t>(8192, 32 * m.efc + 1024);
+        want = std::max(want, 2 * (m.efc + list_cap));
+        a.hash_bits = 10;
+        while ((1ull << a.hash_bits) < want) a.hash_bits++;
+    }
+    const SearchSmem SL(a.efc, (uint32_t)list_cap, a.d4, a.hash_bits);
+    const LinkSmem LL((uint32_t)list_cap + kCapIn);
+    if (SL.total > 226 * 1024) {
+        set_error("ef_construction too large for the build kernel's shared memory");
+        return B200HNSW_E_UNSUPPORTED;
+    }
+    *smem_search = SL.total;
+    *smem_link = LL.total;
+    return 0;
 }
+
 
 // Link every staged point (ids [linked, host.cur)) into the device graph.
 int HnswIndex::flush() {
@@ -450,55 +635,14 @@ int HnswIndex::flush() {
         dev.up_lists = lists;
         B200_CUDA_OK(cudaMemcpy(dev.up_base + linked, base.data(), n_new * 4, cudaMemcpyHostToDevice));
     }
-    // ---- build scratch ----
-    const size_t nl = dev.cap + dev.up_lists_cap;
+    // ---- build scratch + kernel arguments ----
     if (!bld.plevel) B200_CUDA_OK(cudaMalloc(&bld.plevel, std::max<size_t>(dev.cap, 1) * 4));
     B200_CUDA_OK(cudaMemcpy(bld.plevel + linked, m.levels.data() + linked, n_new * 4, cudaMemcpyHostToDevice));
-    if (!bld.incnt) {
-        B200_CUDA_OK(cudaMalloc(&bld.incnt, nl * 4));
-        B200_CUDA_OK(cudaMemset(bld.incnt, 0, nl * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.incoming, nl * kCapIn * 8));
-    }
-    const size_t max_lists = max_batch + max_batch / 2 + 64;  // level-0 list per point + the rare upper lists
-    if (!bld.cand || bld.cand_efc != m.efc) {
-        cudaFree(bld.cand); cudaFree(bld.cand_cnt); cudaFree(bld.list_off); cudaFree(bld.list_point);
-        cudaFree(bld.list_level); cudaFree(bld.aff_node); cudaFree(bld.aff_level); cudaFree(bld.aff_count);
-        cudaFree(bld.work);
-        B200_CUDA_OK(cudaMalloc(&bld.cand, max_lists * m.efc * 8));
-        B200_CUDA_OK(cudaMalloc(&bld.cand_cnt, max_lists * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.list_off, max_batch * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.list_point, max_lists * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.list_level, max_lists * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.aff_node, max_lists * m.M * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.aff_level, max_lists * m.M * 4));
-        B200_CUDA_OK(cudaMalloc(&bld.aff_count, 4));
-        B200_CUDA_OK(cudaMemset(bld.aff_count, 0, 4));
-        B200_CUDA_OK(cudaMalloc(&bld.work, 32));
-        bld.cand_efc = m.efc;
-    }
-    B200_CUDA_OK(cudaMemset(bld.work, 0, 32));
-
-    const size_t list_cap = std::max(m.maxM, m.maxM0);
     BuildArgs a{};
-    a.vec = dev.vec; a.links0 = dev.links0; a.up_base = dev.up_base; a.links_up = dev.links_up;
-    a.plevel = bld.plevel; a.cand = bld.cand; a.cand_cnt = bld.cand_cnt; a.list_off = bld.list_off;
-    a.list_point = bld.list_point; a.list_level = bld.list_level; a.incnt = bld.incnt; a.incoming = bld.incoming;
-    a.aff_node = bld.aff_node; a.aff_level = bld.aff_level; a.aff_count = bld.aff_count; a.work = bld.work;
-    a.cap = (uint32_t)dev.cap; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)m.maxM; a.maxM0 = (uint32_t)m.maxM0;
-    a.M = (uint32_t)m.M; a.efc = (uint32_t)m.efc;
-    // construction searches evaluate ~40 * efc nodes; a table of ~32 * efc slots is rebuilt about once in four searches
-    // and lets twice as many CTAs share an SM as the no-rebuild size (measured: -30 % build time, same graph)
+    size_t max_lists = 0, smem_search = 0, smem_link = 0;
     {
-        size_t want = std::min<size_t>(8192, 32 * m.efc + 1024);
-        want = std::max(want, 2 * (m.efc + list_cap));
-        a.hash_bits = 10;
-        while ((1ull << a.hash_bits) < want) a.hash_bits++;
-    }
-    const SearchSmem SL(a.efc, (uint32_t)list_cap, a.d4, a.hash_bits);
-    const LinkSmem LL((uint32_t)list_cap + kCapIn);
-    if (SL.total > 226 * 1024) {
-        set_error("ef_construction too large for the build kernel's shared memory");
-        return B200HNSW_E_UNSUPPORTED;
+        const int rcp = prepare_build(&a, max_batch, &max_lists, &smem_search, &smem_link);
+        if (rcp) return rcp;
     }
 
     cudaEvent_t e0, e1;
@@ -540,8 +684,8 @@ int HnswIndex::flush() {
         B200_CUDA_OK(cudaMemcpyAsync(bld.list_level, ll.data(), ll.size() * 4, cudaMemcpyHostToDevice, stream));
         a.first = (uint32_t)linked; a.batch = (uint32_t)B; a.lists = (uint32_t)lp.size();
         a.entry = dev_entry; a.maxlevel = dev_maxlevel;
-        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0>(a, SL.total, LL.total, &h_aff, stream)
-                                       : run_batch_metric<1>(a, SL.total, LL.total, &h_aff, stream);
+        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0>(a, smem_search, smem_link, &h_aff, stream)
+                                       : run_batch_metric<1>(a, smem_search, smem_link, &h_aff, stream);
         launches += 3;
         const size_t last = linked + B - 1;
         if (m.levels[last] > dev_maxlevel) {
@@ -573,7 +717,7 @@ int HnswIndex::flush() {
 void BuildScratch::release() {
     cudaFree(plevel); cudaFree(cand); cudaFree(cand_cnt); cudaFree(list_off); cudaFree(list_point);
     cudaFree(list_level); cudaFree(incnt); cudaFree(incoming); cudaFree(aff_node); cudaFree(aff_level);
-    cudaFree(aff_count); cudaFree(work);
+    cudaFree(aff_count); cudaFree(work); cudaFree(batch_ids);
     *this = BuildScratch();
 }
 

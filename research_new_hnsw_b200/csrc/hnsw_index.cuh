@@ -15,7 +15,7 @@ namespace b200 {
 struct BuildScratch {
     int32_t *plevel = nullptr;
     uint64_t *cand = nullptr;
-    uint32_t *cand_cnt = nullptr, *list_off = nullptr, *list_point = nullptr, *list_level = nullptr;
+    uint32_t *cand_cnt = nullptr, *list_off = nullptr, *list_point = nullptr, *list_level = nullptr, *batch_ids = nullptr;
     uint32_t *incnt = nullptr;
     uint64_t *incoming = nullptr;
     uint32_t *aff_node = nullptr, *aff_level = nullptr, *aff_count = nullptr;
@@ -76,6 +76,10 @@ struct HnswIndex {
     // build.cu: addPoint staging and the batched GPU graph build
     int add_batch(const float *X, const uint64_t *labels, size_t n);
     int flush();
+    // build.cu: scratch + batch-independent kernel arguments (args is a BuildArgs*)
+    int prepare_build(void *args, size_t max_batch, size_t *max_lists, size_t *smem_search, size_t *smem_link);
+    // build.cu: updatePoint for ids that are already linked (vectors in the host image are the new ones); mu held
+    int relink_points(std::vector<uint32_t> ids);
     int sync_host_mirror();
 };
 

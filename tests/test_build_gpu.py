@@ -108,7 +108,57 @@ def test_capacity_and_duplicate_label(lib):
         g.addPoint(np.zeros(8, np.float32), 99)
     g2 = lib.HierarchicalNSW(lib.L2Space(8), 10, 4, 20)
     g2.addPoint(np.zeros(8, np.float32), 5)
-    with pytest.raises(lib.B200Error):
-        g2.addPoint(np.ones(8, np.float32), 5)
+    g2.addPoint(np.ones(8, np.float32), 5)                # existing label: updated, not inserted (hnswalg.h:1157)
+    assert g2.cur_element_count == 1 and np.array_equal(g2.getDataByLabel(5), np.ones(8, np.float32))
     r = g.searchKnnBatch(gauss(1, 10, 8), 3, ef=10)
     assert (r["labels"][:, 0] == np.arange(10)).all()
+
+
+@pytest.mark.parametrize("metric", [bind.L2, bind.IP])
+def test_re_adding_labels_updates_points(lib, orc, ref, tmp_path, metric):
+    """addPoint with an existing label = updatePoint (hnswalg.h:1157-1174, 995-1139), batched on the GPU: new vector
+    stored, the point re-linked by the construction kernels in update mode (repairConnectionsForUpdate).  Bars: graph
+    invariants, the moved points are found at their new place, recall within 2 pt of the reference doing the same
+    updates (and of a fresh build of the updated data), the saved file is searched identically by the CPU engine."""
+    n, d, M, efc, nu = 8000, 32, 12, 80, 800
+    ip = metric == bind.IP
+    X = bind.lowrank_data(n, d, seed=81, latent=12, noise=0.15, normalize=ip)
+    Xn = bind.lowrank_data(nu, d, seed=83, latent=12, noise=0.15, normalize=ip)
+    Q = bind.lowrank_data(300, d, seed=82, latent=12, noise=0.15, normalize=ip)
+    upd = np.random.default_rng(84).choice(n, nu, replace=False).astype(np.uint64)
+    X2 = X.copy()
+    X2[upd.astype(np.int64)] = Xn
+    space = lib.L2Space(d) if metric == bind.L2 else lib.InnerProductSpace(d)
+    g = lib.HierarchicalNSW(space, n, M, efc)
+    g.addPoints(X)
+    g.flush()
+    lv_before = g.element_levels_.copy()
+    g.addPoints(Xn, upd)                                          # existing labels -> update
+    assert g.cur_element_count == n and np.array_equal(g.element_levels_, lv_before)
+    assert np.array_equal(g.getDataByLabel(int(upd[0])), Xn[0])
+    _check_graph(g, n, M)
+    bf = orc.bf_new(metric, d, n)
+    bf.add(X2)
+    gt = bf.search(Q, 10)["labels"]
+    rec_g = _recall(g.searchKnnBatch(Q, 10, ef=64)["labels"], gt)
+    fresh = lib.HierarchicalNSW(space, n, M, efc)
+    fresh.addPoints(X2)
+    rec_f = _recall(fresh.searchKnnBatch(Q, 10, ef=64)["labels"], gt)
+    assert rec_g >= rec_f - 0.02, (rec_g, rec_f)
+    if ref is not None:                                           # the unmodified reference doing the same updates
+        c = ref.hnsw_new(metric, d, n, M, efc)
+        c.add(X)
+        c.add(Xn, upd)
+        rec_c = _recall(c.search(Q, 10, 64)["labels"], gt)
+        assert rec_g >= rec_c - 0.02, (rec_g, rec_c)
+    r1 = g.searchKnnBatch(Xn[:200], 1, ef=64)                    # a moved point is its own nearest neighbour
+    assert (r1["labels"][:, 0] == upd[:200]).mean() >= 0.97
+    path = str(tmp_path / "updated.bin")
+    g.saveIndex(path)
+    cpu = orc.hnsw_load(metric, d, path).search(Q, 10, 64)
+    same = np.mean([set(a) == set(b) for a, b in zip(cpu["labels"].tolist(), g.searchKnnBatch(Q, 10, ef=64)["labels"].tolist())])
+    assert same >= 0.99
+    g.markDelete(int(upd[1]))                                     # a deleted label that is re-added is live again
+    g.addPoints(Xn[1:2], upd[1:2])
+    assert g.getDeletedCount() == 0
+    assert g.searchKnnBatch(Xn[1:2], 1, ef=32)["labels"][0, 0] == upd[1]
