@@ -110,6 +110,10 @@ int b200hnsw_set_ef(b200hnsw_index *h, size_t ef);
  * cleared, and the point is re-linked on the GPU (repairConnectionsForUpdate, :1075-1139; the re-pruning of its old
  * neighbours, :1009-1069, is not performed). */
 int b200hnsw_add_batch(b200hnsw_index *h, const float *X, const uint64_t *labels, size_t n);
+/* addPoint(data, label, replace_deleted = true), hnswalg.h:954-992: while deleted elements exist, each row takes the
+ * place of one of them (its label and vector replaced, delete mark cleared, re-linked like an update); otherwise like
+ * b200hnsw_add_batch.  Fails with B200HNSW_E_STATE unless the index was created with allow_replace_deleted. */
+int b200hnsw_add_batch_replace_deleted(b200hnsw_index *h, const float *X, const uint64_t *labels, size_t n);
 /* Links every staged point into the graph on the GPU and refreshes the host mirror. */
 int b200hnsw_flush(b200hnsw_index *h);
 /* searchKnn, hnswalg.h:1270-1324, batched: nq queries of dim floats; ef = 0 -> the setEf value; the engine uses

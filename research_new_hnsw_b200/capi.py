@@ -48,7 +48,7 @@ class _Stats(C.Structure):
 
 EXPORTS = [
     "b200hnsw_last_error", "b200hnsw_abi_version", "b200hnsw_device_count", "b200hnsw_create", "b200hnsw_load",
-    "b200hnsw_save", "b200hnsw_destroy", "b200hnsw_set_ef", "b200hnsw_add_batch", "b200hnsw_flush",
+    "b200hnsw_save", "b200hnsw_destroy", "b200hnsw_set_ef", "b200hnsw_add_batch", "b200hnsw_add_batch_replace_deleted", "b200hnsw_flush",
     "b200hnsw_search_batch", "b200hnsw_search_batch_filtered", "b200hnsw_get_labels", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
     "b200hnsw_get_linklist", "b200hnsw_get_label", "b200hnsw_get_data", "b200hnsw_get_data_by_label",
     "b200hnsw_mark_delete", "b200hnsw_unmark_delete", "b200hnsw_resize", "b200hnsw_index_file_size",
@@ -92,6 +92,7 @@ def load_library():
     L.b200hnsw_destroy.restype = None
     L.b200hnsw_set_ef.argtypes = [vp, sz]
     L.b200hnsw_add_batch.argtypes = [vp, vp, vp, sz]
+    L.b200hnsw_add_batch_replace_deleted.argtypes = [vp, vp, vp, sz]
     L.b200hnsw_flush.argtypes = [vp]
     L.b200hnsw_search_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp]
     L.b200hnsw_search_batch_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp, vp]
@@ -215,15 +216,16 @@ class HierarchicalNSW:
     def setEf(self, ef):
         _chk(self._L.b200hnsw_set_ef(self._h, ef))
 
-    def addPoint(self, datapoint, label):
-        self.addPoints(np.asarray(datapoint, np.float32).reshape(1, -1), np.array([label], np.uint64))
+    def addPoint(self, datapoint, label, replace_deleted=False):
+        self.addPoints(np.asarray(datapoint, np.float32).reshape(1, -1), np.array([label], np.uint64), replace_deleted)
 
-    def addPoints(self, X, labels=None):
+    def addPoints(self, X, labels=None, replace_deleted=False):
         X = np.ascontiguousarray(X, np.float32)
         assert X.ndim == 2 and X.shape[1] == self.space.dim
         if labels is not None:
             labels = np.ascontiguousarray(labels, np.uint64)
-        _chk(self._L.b200hnsw_add_batch(self._h, _ptr(X), _ptr(labels), X.shape[0]))
+        fn = self._L.b200hnsw_add_batch_replace_deleted if replace_deleted else self._L.b200hnsw_add_batch
+        _chk(fn(self._h, _ptr(X), _ptr(labels), X.shape[0]))
 
     def flush(self):
         _chk(self._L.b200hnsw_flush(self._h))

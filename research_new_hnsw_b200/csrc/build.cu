@@ -360,7 +360,7 @@ static size_t env_size(const char *name, size_t dflt) {
 }
 
 // addPoint staging (hnswalg.h:1153-1211,1255-1265): everything that does not need a distance.
-int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n) {
+int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted) {
     std::lock_guard<std::mutex> g(mu);
     HostImage &m = host;
     std::vector<uint32_t> updates;
@@ -381,6 +381,23 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n) {
             }
             memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
             if (c < linked) updates.push_back(c);  // a staged point is simply linked with its new vector later
+            continue;
+        }
+        if (replace_deleted && m.num_deleted > 0) {
+            // vacant place: a deleted element takes the new label and vector (hnswalg.h:965-992)
+            size_t c = replace_scan < m.cur ? replace_scan : 0;
+            while (!m.deleted(c)) c = c + 1 < m.cur ? c + 1 : 0;  // num_deleted > 0: terminates
+            replace_scan = c + 1;
+            uint64_t old_label;
+            memcpy(&old_label, m.rec(c) + m.off_label, 8);
+            m.label_lookup.erase(old_label);
+            m.label_lookup[lab] = (uint32_t)c;
+            memcpy(m.rec(c) + m.off_label, &lab, 8);
+            *((unsigned char *)m.rec(c) + 2) &= (unsigned char)~1;
+            m.num_deleted--;
+            flags_dirty = true;
+            memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
+            if (c < linked) updates.push_back((uint32_t)c);
             continue;
         }
         if (m.cur >= m.max_elements) {
@@ -422,6 +439,7 @@ int HnswIndex::relink_points(std::vector<uint32_t> ids) {
         for (uint32_t id : ids) {
             memcpy(row.data(), m.rec(id) + m.off_data, m.dim * 4);
             B200_CUDA_OK(cudaMemcpy((float *)dev.vec + (size_t)id * dev.d4 * 4, row.data(), dev.d4 * 16, cudaMemcpyHostToDevice));
+            B200_CUDA_OK(cudaMemcpy(dev.labels + id, m.rec(id) + m.off_label, 8, cudaMemcpyHostToDevice));  // replace_deleted relabels
             const int rc16 = sync_bf16(id, 1);
             if (rc16) return rc16;
         }

@@ -127,6 +127,17 @@ int b200hnsw_add_batch(b200hnsw_index *h, const float *X, const uint64_t *labels
     B200_GUARD_END
 }
 
+int b200hnsw_add_batch_replace_deleted(b200hnsw_index *h, const float *X, const uint64_t *labels, size_t n) {
+    B200_GUARD_BEGIN
+    if (!h || (!X && n)) { set_error("null argument"); return B200HNSW_E_ARG; }
+    if (!h->ix.prm.allow_replace_deleted) {
+        set_error("Replacement of deleted elements is disabled in constructor");  // hnswalg.h:955-957
+        return B200HNSW_E_STATE;
+    }
+    return h->ix.add_batch(X, labels, n, true);
+    B200_GUARD_END
+}
+
 int b200hnsw_flush(b200hnsw_index *h) {
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }

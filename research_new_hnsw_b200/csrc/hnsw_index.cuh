@@ -74,7 +74,8 @@ struct HnswIndex {
     int search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
                     uint32_t *counts, uint32_t *work, const uint8_t *allowed = nullptr);
     // build.cu: addPoint staging and the batched GPU graph build
-    int add_batch(const float *X, const uint64_t *labels, size_t n);
+    int add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted = false);
+    size_t replace_scan = 0;  // where the search for a deleted slot resumes (replace_deleted)
     int flush();
     // build.cu: scratch + batch-independent kernel arguments (args is a BuildArgs*)
     int prepare_build(void *args, size_t max_batch, size_t *max_lists, size_t *smem_search, size_t *smem_link);

@@ -493,13 +493,14 @@ class HierarchicalNSW : public AlgorithmInterface<dist_t> {
     // maxlevel_ are updated immediately (they depend only on the level generator), graph links are built on the GPU
     // in batches at the next searchKnn / saveIndex / get_linklist* / flush().
     void addPoint(const void *data_point, labeltype label, bool replace_deleted = false) {
+        uint64_t lab = label;
         if (replace_deleted) {
             if (!allow_replace_deleted_)
                 throw std::runtime_error("Replacement of deleted elements is disabled in constructor");
-            throw std::runtime_error("replace_deleted is not supported by the GPU engine");
+            b200detail::check(b200hnsw_add_batch_replace_deleted(h_, (const float *)data_point, &lab, 1));
+        } else {
+            b200detail::check(b200hnsw_add_batch(h_, (const float *)data_point, &lab, 1));
         }
-        uint64_t lab = label;
-        b200detail::check(b200hnsw_add_batch(h_, (const float *)data_point, &lab, 1));
         after_add(1);
     }
     // batched extension (not in the reference): n rows in one call

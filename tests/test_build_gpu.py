@@ -162,3 +162,44 @@ def test_re_adding_labels_updates_points(lib, orc, ref, tmp_path, metric):
     g.addPoints(Xn[1:2], upd[1:2])
     assert g.getDeletedCount() == 0
     assert g.searchKnnBatch(Xn[1:2], 1, ef=32)["labels"][0, 0] == upd[1]
+
+
+def test_replace_deleted_reuses_slots(lib, orc):
+    """addPoint(data, label, replace_deleted=true) (hnswalg.h:954-992): a deleted element's slot takes the new label and
+    vector and is re-linked; element count and levels do not change; without the constructor flag the call fails."""
+    n, d, M, efc, nd = 4000, 24, 10, 60, 400
+    X = bind.lowrank_data(n, d, seed=91, latent=10, noise=0.15)
+    Xn = bind.lowrank_data(nd + 5, d, seed=92, latent=10, noise=0.15)
+    Q = bind.lowrank_data(200, d, seed=93, latent=10, noise=0.15)
+    g = lib.HierarchicalNSW(lib.L2Space(d), n + 5, M, efc, allow_replace_deleted=True)
+    g.addPoints(X)
+    g.flush()
+    dead = np.sort(np.random.default_rng(94).choice(n, nd, replace=False))
+    for l in dead.tolist():
+        g.markDelete(l)
+    assert g.getDeletedCount() == nd
+    new_labels = np.arange(10_000, 10_000 + nd + 5, dtype=np.uint64)
+    g.addPoints(Xn, new_labels, replace_deleted=True)             # 400 slots reused, 5 points appended
+    assert g.cur_element_count == n + 5 and g.getDeletedCount() == 0
+    with pytest.raises(lib.B200Error):
+        g.getDataByLabel(int(dead[0]))
+    assert np.array_equal(g.getDataByLabel(10_000), Xn[0])
+    assert g.getExternalLabel(int(dead[0])) == 10_000             # slots are taken in ascending order
+    _check_graph(g, n + 5, M)
+    X2 = np.concatenate([X, Xn[nd:]])
+    L2 = np.concatenate([np.arange(n, dtype=np.uint64), new_labels[nd:]])
+    X2[dead] = Xn[:nd]
+    L2[dead] = new_labels[:nd]
+    bf = orc.bf_new(bind.L2, d, n + 5)
+    bf.add(X2, L2)
+    gt = bf.search(Q, 10)["labels"]
+    rec_g = _recall(g.searchKnnBatch(Q, 10, ef=64)["labels"], gt)
+    fresh = lib.HierarchicalNSW(lib.L2Space(d), n + 5, M, efc)
+    fresh.addPoints(X2, L2)
+    rec_f = _recall(fresh.searchKnnBatch(Q, 10, ef=64)["labels"], gt)
+    assert rec_g >= rec_f - 0.02, (rec_g, rec_f)
+    r1 = g.searchKnnBatch(Xn[:100], 1, ef=64)
+    assert (r1["labels"][:, 0] == new_labels[:100]).mean() >= 0.97
+    g0 = lib.HierarchicalNSW(lib.L2Space(d), 10, 4, 20)
+    with pytest.raises(lib.B200Error, match="disabled in constructor"):
+        g0.addPoints(X[:1], replace_deleted=True)
