@@ -1,0 +1,15 @@
+#!/usr/bin/env python
+"""GPU build of the C2 data set only (1M x 128, M=32, efc=200), twice; B200HNSW_LIB selects the library (A/B)."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import research_new_hnsw_b200 as pkg
+from research_new_hnsw_b200.synth import lowrank_data
+X = lowrank_data(1_000_000, 128, seed=1)
+for rep in range(2):
+    g = pkg.HierarchicalNSW(pkg.L2Space(128), len(X), 32, 200)
+    t = time.time(); g.addPoints(X); g.flush(); sec = time.time() - t
+    st = g.stats()
+    print("%s rep %d: %.2f s (%.0f pts/s), flush events %.0f ms, D/pt %.1f" % (
+        os.path.basename(os.environ.get("B200HNSW_LIB", "head")), rep, sec, len(X) / sec, st["last_kernel_ms"], st["dist_evals"] / len(X)), flush=True)
+    del g
