@@ -43,12 +43,13 @@ struct BuildArgs {
     uint64_t *incoming;        // [cap + up_lists_cap][kCapIn]
     uint32_t *aff_node, *aff_level, *aff_count;
     unsigned long long *work;  // [4] D, H0, Hup, resets (atomicAdd)
-    const uint32_t *batch_ids;  // update mode: ids of the (already linked) points of this batch; else first + b
-    uint32_t update;            // 1: re-link existing points (repairConnectionsForUpdate, hnswalg.h:1075-1139)
     uint32_t cap, first, batch, lists;
     uint32_t entry;
     int32_t maxlevel;
     uint32_t d4, maxM, maxM0, M, efc, hash_bits;
+    // update mode only (kernels instantiated with UPD = true re-link EXISTING points: repairConnectionsForUpdate,
+    // hnswalg.h:1075-1139); kept at the end so the insert-mode kernels see the layout they were tuned with
+    const uint32_t *batch_ids;  // [batch] ids of the points of this batch (insert mode: first + b)
 };
 
 template <int LPV, int CPL>
@@ -61,7 +62,7 @@ __device__ __forceinline__ void load_row(float4 (&v)[CPL], const float4 *row, ui
 }
 
 // Construction search for one new point: CTA b handles point first + b on all of its levels.
-template <int LPV, int CPL, int METRIC>
+template <int LPV, int CPL, int METRIC, bool UPD>
 __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
 
     const int tid = threadIdx.x;
     const int sub = tid % LPV, grp = tid / LPV;
-    const uint32_t pid = p.batch_ids ? p.batch_ids[blockIdx.x] : p.first + blockIdx.x;
+    const uint32_t pid = UPD ? p.batch_ids[blockIdx.x] : p.first + blockIdx.x;
     const uint32_t HS = 1u << p.hash_bits;
     const int plevel = p.plevel[pid];
 
@@ -170,7 +171,7 @@ __device__ __forceinline__ uint32_t *list_ptr(const BuildArgs &p, uint32_t node,
 }
 
 // One CTA per (new point, level): prune the candidates to M, write the forward list, stage the reverse edges.
-template <int LPV, int CPL, int METRIC>
+template <int LPV, int CPL, int METRIC, bool UPD>
 __global__ void __launch_bounds__(kTeam) build_link_kernel(const BuildArgs p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t capc = max(p.maxM0, p.maxM) + kCapIn;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(kTeam) build_link_kernel(const BuildArgs p) {
     const uint32_t pid = p.list_point[slot], level = p.list_level[slot];
     int n = (int)p.cand_cnt[slot];
     uint64_t *cand = p.cand + (size_t)slot * p.efc;
-    if (p.update) {
+    if constexpr (UPD) {
         // the point is already in the graph, so its own search finds it: drop it from the candidates
         // (filteredTopCandidates, hnswalg.h:1117-1123) by closing the gap in the sorted list
         __shared__ int s_self;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kTeam) build_link_kernel(const BuildArgs p) {
     uint32_t evals = 0;
     const int ns = heuristic_prune<LPV, CPL, METRIC>(g, cand, n, (int)p.M, sel, ids, dist, evals);
     uint32_t *mine = list_ptr(p, pid, level);
-    if (p.update) {  // the old forward list is replaced, not extended
+    if constexpr (UPD) {  // the old forward list is replaced, not extended
         const int Mcur = (int)(level ? p.maxM : p.maxM0);
         for (int j = ns + tid; j < Mcur; j += kTeam) mine[j] = kEmpty;
     }
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kTeam) build_link_kernel(const BuildArgs p) {
 
 // One CTA per touched list: append the incoming new points while there is room, otherwise re-run the heuristic over
 // existing + incoming neighbours (distances to this node) and rewrite the list.
-template <int LPV, int CPL, int METRIC>
+template <int LPV, int CPL, int METRIC, bool UPD>
 __global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p, uint32_t n_aff) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t capc = max(p.maxM0, p.maxM) + kCapIn;
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p,
     for (int j = tid; j < t; j += kTeam) raw[deg + j] = p.incoming[(size_t)lid * kCapIn + j];
     __syncthreads();
     if (tid == 0) p.incnt[lid] = 0;  // ready for the next batch
-    if (p.update) {
+    if constexpr (UPD) {
         // a re-linked point may already be a neighbour of this node (is_cur_c_present, hnswalg.h:566-580): keep the
         // existing edge, drop the incoming duplicate
         __shared__ int s_keep;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p,
     if (tid == 0) atomicAdd(p.work + 0, (unsigned long long)evals);
 }
 
-template <int LPV, int CPL, int METRIC>
+template <int LPV, int CPL, int METRIC, bool UPD>
 static int run_batch(const BuildArgs &a, size_t smem_search, size_t smem_link, uint32_t *h_aff, cudaStream_t st) {
     static bool configured[16] = {};
     int d = 0;
@@ -316,35 +317,35 @@ static int run_batch(const BuildArgs &a, size_t smem_search, size_t smem_link, u
         cudaFuncAttributes fa;
         int optin = 0;
         B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, build_search_kernel<LPV, CPL, METRIC>));
-        B200_CUDA_OK(cudaFuncSetAttribute(build_search_kernel<LPV, CPL, METRIC>,
+        B200_CUDA_OK(cudaFuncGetAttributes(&fa, build_search_kernel<LPV, CPL, METRIC, UPD>));
+        B200_CUDA_OK(cudaFuncSetAttribute(build_search_kernel<LPV, CPL, METRIC, UPD>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
-    build_search_kernel<LPV, CPL, METRIC><<<a.batch, kTeam, smem_search, st>>>(a);
-    build_link_kernel<LPV, CPL, METRIC><<<a.lists, kTeam, smem_link, st>>>(a);
+    build_search_kernel<LPV, CPL, METRIC, UPD><<<a.batch, kTeam, smem_search, st>>>(a);
+    build_link_kernel<LPV, CPL, METRIC, UPD><<<a.lists, kTeam, smem_link, st>>>(a);
     B200_CUDA_OK(cudaMemcpyAsync(h_aff, a.aff_count, 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     const uint32_t n_aff = *h_aff;
-    if (n_aff) build_reverse_kernel<LPV, CPL, METRIC><<<n_aff, kTeam, smem_link, st>>>(a, n_aff);
+    if (n_aff) build_reverse_kernel<LPV, CPL, METRIC, UPD><<<n_aff, kTeam, smem_link, st>>>(a, n_aff);
     B200_CUDA_OK(cudaMemsetAsync(a.aff_count, 0, 4, st));
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-template <int METRIC>
+template <int METRIC, bool UPD = false>
 static int run_batch_metric(const BuildArgs &a, size_t s1, size_t s2, uint32_t *h_aff, cudaStream_t st) {
     const uint32_t d4 = a.d4;
-    if (d4 <= 8) return run_batch<8, 1, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 16) return run_batch<8, 2, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 24) return run_batch<8, 3, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 32) return run_batch<8, 4, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 48) return run_batch<16, 3, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 64) return run_batch<16, 4, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 96) return run_batch<32, 3, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 128) return run_batch<32, 4, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 192) return run_batch<32, 6, METRIC>(a, s1, s2, h_aff, st);
-    if (d4 <= 256) return run_batch<32, 8, METRIC>(a, s1, s2, h_aff, st);
+    if (d4 <= 8) return run_batch<8, 1, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 16) return run_batch<8, 2, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 24) return run_batch<8, 3, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 32) return run_batch<8, 4, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 48) return run_batch<16, 3, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 64) return run_batch<16, 4, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 96) return run_batch<32, 3, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 128) return run_batch<32, 4, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 192) return run_batch<32, 6, METRIC, UPD>(a, s1, s2, h_aff, st);
+    if (d4 <= 256) return run_batch<32, 8, METRIC, UPD>(a, s1, s2, h_aff, st);
     set_error("dimension > 1024 is not supported by the build kernels");
     return B200HNSW_E_UNSUPPORTED;
 }
@@ -476,9 +477,9 @@ int HnswIndex::relink_points(std::vector<uint32_t> ids) {
         B200_CUDA_OK(cudaMemcpyAsync(bld.list_level, ll.data(), ll.size() * 4, cudaMemcpyHostToDevice, stream));
         a.first = 0; a.batch = (uint32_t)B; a.lists = (uint32_t)lp.size();
         a.entry = dev_entry; a.maxlevel = dev_maxlevel;
-        a.batch_ids = bld.batch_ids; a.update = 1;
-        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0>(a, smem_search, smem_link, &h_aff, stream)
-                                       : run_batch_metric<1>(a, smem_search, smem_link, &h_aff, stream);
+        a.batch_ids = bld.batch_ids;
+        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0, true>(a, smem_search, smem_link, &h_aff, stream)
+                                       : run_batch_metric<1, true>(a, smem_search, smem_link, &h_aff, stream);
         launches += 3;
         b0 += B;
     }
