@@ -88,6 +88,9 @@ class Ref(_Lib):
         L.ref_hnsw_levels.argtypes = [C.c_void_p, _i32p]
         L.ref_hnsw_links.argtypes = [C.c_void_p, C.c_uint32, C.c_int, _u32p, C.c_int]
         L.ref_hnsw_mark_delete.argtypes = [C.c_void_p, C.c_uint64]
+        L.ref_hnsw_new_replace.restype = C.c_void_p
+        L.ref_hnsw_new_replace.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.ref_hnsw_add_replace_deleted.argtypes = [C.c_void_p, _f32p, C.c_void_p, C.c_size_t]
         L.ref_hnsw_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                       _u64p, _f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.ref_bf_new.restype = C.c_void_p
@@ -120,8 +123,11 @@ class Ref(_Lib):
         b = np.ascontiguousarray(b, np.float32)
         return float(self.lib.ref_dist(metric, a.size, a, b))
 
-    def hnsw_new(self, metric, dim, max_elements, M=16, efc=200, seed=100, counting=False):
-        h = self.lib.ref_hnsw_new(metric, dim, max_elements, M, efc, seed, int(counting))
+    def hnsw_new(self, metric, dim, max_elements, M=16, efc=200, seed=100, counting=False, allow_replace_deleted=False):
+        if allow_replace_deleted:
+            h = self.lib.ref_hnsw_new_replace(metric, dim, max_elements, M, efc, seed)
+        else:
+            h = self.lib.ref_hnsw_new(metric, dim, max_elements, M, efc, seed, int(counting))
         if not h:
             raise RuntimeError(self.err())
         return RefHnsw(self, h, dim)
@@ -165,6 +171,12 @@ class RefHnsw:
         sec = C.c_double(0)
         self._chk(self.ref.lib.ref_hnsw_add(self.h, X, _opt(labels), X.shape[0], threads, C.byref(sec)))
         return sec.value
+
+    def add_replace_deleted(self, X, labels):
+        """addPoint(data, label, replace_deleted=True), serial"""
+        X = np.ascontiguousarray(X, np.float32)
+        labels = np.ascontiguousarray(labels, np.uint64)
+        self._chk(self.ref.lib.ref_hnsw_add_replace_deleted(self.h, X, _opt(labels), X.shape[0]))
 
     def save(self, path):
         self._chk(self.ref.lib.ref_hnsw_save(self.h, path.encode()))
@@ -270,6 +282,8 @@ class Oracle(_Lib):
         L.orc_hnsw_levels.argtypes = [C.c_void_p, _i32p]
         L.orc_hnsw_links.argtypes = [C.c_void_p, C.c_uint32, C.c_int, _u32p, C.c_int]
         L.orc_hnsw_mark_delete.argtypes = [C.c_void_p, C.c_uint64]
+        L.orc_hnsw_allow_replace_deleted.argtypes = [C.c_void_p, C.c_int]
+        L.orc_hnsw_add_replace_deleted.argtypes = [C.c_void_p, _f32p, C.c_void_p, C.c_size_t]
         L.orc_hnsw_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _f32p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
         L.orc_bf_new.restype = C.c_void_p
@@ -288,14 +302,19 @@ class Oracle(_Lib):
         b = np.ascontiguousarray(b, np.float32)
         return float(self.lib.orc_dist(metric, a.size, a, b))
 
-    def hnsw_new(self, metric, dim, max_elements, M=16, efc=200, seed=100):
-        return OrcHnsw(self, self.lib.orc_hnsw_new(metric, dim, max_elements, M, efc, seed), dim)
+    def hnsw_new(self, metric, dim, max_elements, M=16, efc=200, seed=100, allow_replace_deleted=False):
+        h = OrcHnsw(self, self.lib.orc_hnsw_new(metric, dim, max_elements, M, efc, seed), dim)
+        if allow_replace_deleted:
+            self.lib.orc_hnsw_allow_replace_deleted(h.h, 1)
+        return h
 
-    def hnsw_load(self, metric, dim, path, max_elements=0):
+    def hnsw_load(self, metric, dim, path, max_elements=0, allow_replace_deleted=False):
         rc = C.c_int(0)
         h = self.lib.orc_hnsw_load(metric, dim, path.encode(), max_elements, C.byref(rc))
         if not h:
             raise RuntimeError({-1: "Cannot open file", -2: "Index seems to be corrupted or unsupported"}[rc.value])
+        if allow_replace_deleted:
+            self.lib.orc_hnsw_allow_replace_deleted(h, 1)
         return OrcHnsw(self, h, dim)
 
     def bf_new(self, metric, dim, max_elements):
@@ -320,6 +339,15 @@ class OrcHnsw:
             raise RuntimeError("The number of elements exceeds the specified limit")
         if rc:
             raise RuntimeError("oracle add_point rc=%d" % rc)
+
+    def add_replace_deleted(self, X, labels):
+        X = np.ascontiguousarray(X, np.float32)
+        labels = np.ascontiguousarray(labels, np.uint64)
+        rc = self.orc.lib.orc_hnsw_add_replace_deleted(self.h, X, _opt(labels), X.shape[0])
+        if rc == -3:
+            raise RuntimeError("Replacement of deleted elements is disabled in constructor")
+        if rc:
+            raise RuntimeError("oracle add_point_replace rc=%d" % rc)
 
     def save(self, path):
         if self.orc.lib.orc_hnsw_save(self.h, path.encode()):

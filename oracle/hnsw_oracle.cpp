@@ -1,8 +1,8 @@
 // oracle/hnsw_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 //
 // CPU restatement (own code, written from the algorithm, not copied) of the reference hot
-// path: distance spaces, saveIndex/loadIndex byte format, searchKnn, serial addPoint and
-// BruteforceSearch.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+// path: distance spaces, saveIndex/loadIndex byte format, searchKnn, serial addPoint (including
+// updatePoint for an existing label and replace_deleted) and BruteforceSearch.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
 // load this library; the product (libb200hnsw.so) never links or calls it.
 //
 // PARITY PINNED: tests/test_oracle.py checks this restatement against (a) the golden
@@ -24,6 +24,7 @@
 #include <random>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 namespace orc {
@@ -133,6 +134,8 @@ struct Index {
     std::unordered_map<uint64_t, tableint> label_lookup;
     std::default_random_engine level_rng;  // hnswalg.h:62,117
     size_t num_deleted = 0;
+    bool allow_replace_deleted = false;               // hnswalg.h:73,93
+    std::unordered_set<tableint> deleted_elements;    // hnswalg.h:75 (filled only with allow_replace_deleted)
     // counters (hnswalg.h:65-66 metric_* analogues)
     mutable uint64_t c_dist = 0, c_hops0 = 0, c_hops_up = 0;
 
@@ -250,8 +253,8 @@ struct Index {
         for (const cand_t &c : keep) top.emplace(-c.first, c.second);
     }
 
-    // hnswalg.h:506-630 (isUpdate == false path)
-    tableint connect(tableint cur_c, heap_t &top, int level) {
+    // hnswalg.h:506-630; is_update: the list of cur_c is replaced, a neighbour that already lists cur_c is left alone
+    tableint connect(tableint cur_c, heap_t &top, int level, bool is_update = false) {
         size_t Mcur = level ? maxM : maxM0;
         heuristic(top, M);
         std::vector<tableint> sel;
@@ -267,6 +270,11 @@ struct Index {
             uint32_t *lo = list(sel[i], level);
             size_t sz = count_of(lo);
             uint32_t *data = lo + 1;
+            if (is_update) {  // is_cur_c_present, hnswalg.h:566-580
+                bool present = false;
+                for (size_t j = 0; j < sz; j++) present |= data[j] == cur_c;
+                if (present) continue;
+            }
             if (sz < Mcur) {
                 data[sz] = cur_c;
                 set_count(lo, (unsigned short)(sz + 1));
@@ -290,9 +298,127 @@ struct Index {
     std::vector<uint32_t> visited_build;
     uint32_t visited_tag = 0;
 
-    // hnswalg.h:1153-1267, new-label path only (no update / replace-deleted)
+    void unmark_deleted(tableint id) {  // hnswalg.h:903-917
+        ((unsigned char *)rec(id))[2] &= (unsigned char)~1;
+        num_deleted--;
+        if (allow_replace_deleted) deleted_elements.erase(id);
+    }
+
+    // updatePoint, hnswalg.h:995-1072, updateNeighborProbability = 1.0 (the value addPoint passes).  The containers are
+    // the reference's (unordered sets iterated in their own order, max-heaps compared by distance only) so that ties
+    // resolve the same way.
+    void update_point(const float *x, tableint id) {
+        memcpy(rec(id) + off_data, x, dim * 4);
+        int max_level_copy = maxlevel;
+        tableint entry_copy = enterpoint;
+        if (entry_copy == id && cur == 1) return;
+        int elem_level = levels[id];
+        for (int layer = 0; layer <= elem_level; layer++) {
+            std::unordered_set<tableint> s_cand, s_neigh;
+            const uint32_t *l1 = list(id, layer);
+            std::vector<tableint> one_hop(l1 + 1, l1 + 1 + count_of(l1));
+            if (one_hop.empty()) continue;
+            s_cand.insert(id);
+            for (tableint el : one_hop) {
+                s_cand.insert(el);
+                s_neigh.insert(el);
+                const uint32_t *l2 = list(el, layer);
+                unsigned n2 = count_of(l2);
+                for (unsigned j = 1; j <= n2; j++) s_cand.insert(l2[j]);
+            }
+            for (tableint neigh : s_neigh) {
+                heap_t cands;
+                size_t size = s_cand.find(neigh) == s_cand.end() ? s_cand.size() : s_cand.size() - 1;
+                size_t keep = std::min(efc, size);
+                for (tableint c : s_cand) {
+                    if (c == neigh) continue;
+                    float d = dist(vec(neigh), vec(c));
+                    if (cands.size() < keep) {
+                        cands.emplace(d, c);
+                    } else if (d < cands.top().first) {
+                        cands.pop();
+                        cands.emplace(d, c);
+                    }
+                }
+                heuristic(cands, layer == 0 ? maxM0 : maxM);
+                uint32_t *ln = list(neigh, layer);
+                size_t cs = cands.size();
+                set_count(ln, (unsigned short)cs);
+                for (size_t idx = 0; idx < cs; idx++) {
+                    ln[1 + idx] = cands.top().second;
+                    cands.pop();
+                }
+            }
+        }
+        repair_connections(x, entry_copy, id, elem_level, max_level_copy);
+    }
+
+    // repairConnectionsForUpdate, hnswalg.h:1075-1139
+    void repair_connections(const float *x, tableint entry, tableint id, int elem_level, int max_level) {
+        tableint cur_obj = entry;
+        if (elem_level < max_level) {
+            float curdist = dist(x, vec(cur_obj));
+            for (int level = max_level; level > elem_level; level--) {
+                bool changed = true;
+                while (changed) {
+                    changed = false;
+                    const uint32_t *l = list(cur_obj, level);
+                    unsigned n = count_of(l);
+                    for (unsigned i = 1; i <= n; i++) {
+                        float d = dist(x, vec(l[i]));
+                        if (d < curdist) {
+                            curdist = d;
+                            cur_obj = l[i];
+                            changed = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (visited_build.size() != max_elements) visited_build.assign(max_elements, 0);
+        for (int level = elem_level; level >= 0; level--) {
+            ++visited_tag;
+            heap_t top = search_layer_build(cur_obj, x, level, visited_build, visited_tag);
+            heap_t filtered;
+            while (!top.empty()) {
+                if (top.top().second != id) filtered.push(top.top());
+                top.pop();
+            }
+            if (!filtered.empty()) {
+                if (deleted(entry)) {
+                    filtered.emplace(dist(x, vec(entry)), entry);
+                    if (filtered.size() > efc) filtered.pop();
+                }
+                cur_obj = connect(id, filtered, level, true);
+            }
+        }
+    }
+
+    // addPoint(data, label, replace_deleted = true), hnswalg.h:954-992.  Returns -3 when replacement is disabled.
+    int add_point_replace(const float *x, uint64_t lab) {
+        if (!allow_replace_deleted) return -3;
+        if (deleted_elements.empty()) return add_point(x, lab);
+        tableint id = *deleted_elements.begin();
+        deleted_elements.erase(id);
+        uint64_t old = label(id);
+        memcpy(rec(id) + off_label, &lab, 8);
+        label_lookup.erase(old);
+        label_lookup[lab] = id;
+        unmark_deleted(id);
+        update_point(x, id);
+        return 0;
+    }
+
+    // hnswalg.h:1153-1267; an existing label is updated (:1157-1174)
     int add_point(const float *x, uint64_t lab) {
-        if (label_lookup.count(lab)) return -2;  // updatePoint is outside the restated path
+        auto known = label_lookup.find(lab);
+        if (known != label_lookup.end()) {
+            tableint id = known->second;
+            if (allow_replace_deleted && deleted(id)) return -4;  // "Can't use addPoint to update deleted elements ..."
+            if (deleted(id)) unmark_deleted(id);
+            update_point(x, id);
+            return 0;
+        }
         if (cur >= max_elements) return -1;      // "The number of elements exceeds the specified limit"
         tableint cur_c = (tableint)cur++;
         label_lookup[lab] = cur_c;
@@ -639,6 +765,18 @@ int orc_hnsw_mark_delete(void *h, uint64_t label) {  // hnswalg.h:853-883
     if (*p & 1) return -2;
     *p |= 1;
     ix->num_deleted++;
+    if (ix->allow_replace_deleted) ix->deleted_elements.insert(it->second);  // hnswalg.h:876-879
+    return 0;
+}
+
+void orc_hnsw_allow_replace_deleted(void *h, int on) { ((orc::Index *)h)->allow_replace_deleted = on != 0; }
+
+int orc_hnsw_add_replace_deleted(void *h, const float *X, const uint64_t *labels, size_t n) {
+    orc::Index *ix = (orc::Index *)h;
+    for (size_t i = 0; i < n; i++) {
+        int r = ix->add_point_replace(X + i * ix->dim, labels ? labels[i] : i);
+        if (r) return r;
+    }
     return 0;
 }
 

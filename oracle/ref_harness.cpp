@@ -245,6 +245,28 @@ int ref_hnsw_links(void *h, uint32_t id, int level, uint32_t *out, int cap) {
     return cnt;
 }
 
+// Same as ref_hnsw_new with allow_replace_deleted (hnswalg.h:89-99).
+void *ref_hnsw_new_replace(int metric, size_t dim, size_t max_elements, size_t M, size_t efc, size_t seed) {
+    RefIndex *r = nullptr;
+    int rc = guarded([&] {
+        r = new RefIndex();
+        r->dim = dim;
+        r->counting = false;
+        r->space.reset(make_space(metric, dim));
+        r->alg.reset(new hnswlib::HierarchicalNSW<float>(r->space.get(), max_elements, M, efc, seed, true));
+    });
+    if (rc) { delete r; return nullptr; }
+    return r;
+}
+
+// addPoint(data, label, replace_deleted = true), serial (hnswalg.h:954-992)
+int ref_hnsw_add_replace_deleted(void *h, const float *X, const uint64_t *labels, size_t n) {
+    RefIndex *r = (RefIndex *)h;
+    return guarded([&] {
+        for (size_t i = 0; i < n; i++) r->alg->addPoint(X + i * r->dim, labels ? labels[i] : (hnswlib::labeltype)i, true);
+    });
+}
+
 int ref_hnsw_mark_delete(void *h, uint64_t label) {
     RefIndex *r = (RefIndex *)h;
     return guarded([&] { r->alg->markDelete(label); });

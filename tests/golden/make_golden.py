@@ -19,10 +19,59 @@ from oracle import bind  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def update_inputs(c):
+    """Seeded inputs of the updatePoint / replace_deleted fixtures (shared with tests/test_oracle.py)."""
+    rng = np.random.default_rng(789 + c["n"])
+    nu = c["n"] // 10
+    return dict(nu=nu, upd=rng.choice(c["n"], nu, replace=False).astype(np.uint64),
+                Xn=rng.standard_normal((nu, c["d"]), dtype=np.float32),
+                dead=rng.choice(c["n"], nu, replace=False),
+                new_labels=np.arange(100000, 100000 + nu, dtype=np.uint64),
+                Xr=rng.standard_normal((nu, c["d"]), dtype=np.float32))
+
+
+UPDATE_CASES = [dict(name="l2_n2000_d16_M8", metric=bind.L2, n=2000, d=16, M=8, efc=100),
+                dict(name="ip_n1500_d24_M6", metric=bind.IP, n=1500, d=24, M=6, efc=60),
+                dict(name="l2_n1200_d13_M5", metric=bind.L2, n=1200, d=13, M=5, efc=40)]
+
+
+def update_golden(ref):
+    """sha256 of the reference's saveIndex file after (a) re-adding n/10 existing labels with new vectors
+    (addPoint -> updatePoint, hnswalg.h:1157-1174, 995-1139) and (b) marking n/10 elements deleted and adding n/10 new
+    labels with replace_deleted = true (hnswalg.h:954-992) -> tests/golden/update_golden.json."""
+    out = {}
+    for c in UPDATE_CASES:
+        X = ref.gen_gaussian(123, c["n"], c["d"])
+        if c["metric"] == bind.IP:
+            X /= np.linalg.norm(X, axis=1, keepdims=True)
+        u = update_inputs(c)
+        tmp = os.path.join(OUT, "_tmp_update.bin")
+        idx = ref.hnsw_new(c["metric"], c["d"], c["n"], c["M"], c["efc"], 100)
+        idx.add(X)
+        idx.add(u["Xn"], u["upd"])
+        idx.save(tmp)
+        sha_u = hashlib.sha256(open(tmp, "rb").read()).hexdigest()
+        idx = ref.hnsw_new(c["metric"], c["d"], c["n"], c["M"], c["efc"], 100, allow_replace_deleted=True)
+        idx.add(X)
+        for l in u["dead"].tolist():
+            idx.mark_delete(l)
+        idx.add_replace_deleted(u["Xr"], u["new_labels"])
+        idx.save(tmp)
+        sha_r = hashlib.sha256(open(tmp, "rb").read()).hexdigest()
+        os.remove(tmp)
+        out[c["name"]] = dict(update_sha256=sha_u, replace_deleted_sha256=sha_r)
+    json.dump(out, open(os.path.join(OUT, "update_golden.json"), "w"), indent=1, sort_keys=True)
+    return out
+
+
 def main():
     bind.build()
     ref = bind.Ref("sse")
     assert ref.simd_level() == "sse"
+    if "--updates-only" in sys.argv:
+        print(update_golden(ref))
+        return
+    update_golden(ref)
     meta = {}
     arrays = {}
 

@@ -1,7 +1,9 @@
 """CPU: pin the oracle (own restatement) to the reference's known answers, golden outputs and, when the compiled
 reference is present (oracle/_ref), to the reference itself on fresh seeded inputs."""
 import hashlib
+import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -100,6 +102,34 @@ def test_build_reproduces_survey_known_answer(orc, ref, golden, tmp_path):
     assert (info["enterpoint"], info["maxlevel"]) == (4373, 3)
 
 
+@pytest.mark.parametrize("name", ["l2_n2000_d16_M8", "ip_n1500_d24_M6", "l2_n1200_d13_M5"])
+def test_update_and_replace_deleted_match_reference_fixture(orc, golden, name, tmp_path):
+    """updatePoint (addPoint with an existing label, hnswalg.h:1157-1174 -> 995-1139) and replace_deleted (:954-992):
+    the saved file after the reference applied the seeded changes (tests/golden/update_golden.json, written by
+    make_golden.py) must be reproduced byte for byte by the restatement starting from the committed index file."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    meta, _ = golden
+    m = meta[name]
+    u = make_golden.update_inputs(dict(n=m["n"], d=m["d"]))
+    fx = json.load(open(os.path.join(GOLDEN, "update_golden.json")))[name]
+    src = os.path.join(GOLDEN, name + ".bin")
+    out = str(tmp_path / "changed.bin")
+    idx = orc.hnsw_load(m["metric"], m["d"], src)
+    idx.add(u["Xn"], u["upd"])
+    idx.save(out)
+    assert _sha(out) == fx["update_sha256"]
+    idx = orc.hnsw_load(m["metric"], m["d"], src, allow_replace_deleted=True)
+    for l in u["dead"].tolist():
+        idx.mark_delete(l)
+    idx.add_replace_deleted(u["Xr"], u["new_labels"])
+    idx.save(out)
+    assert _sha(out) == fx["replace_deleted_sha256"]
+    plain = orc.hnsw_load(m["metric"], m["d"], src)
+    with pytest.raises(RuntimeError, match="disabled in constructor"):
+        plain.add_replace_deleted(u["Xr"][:1], u["new_labels"][:1])
+
+
 @pytest.mark.parametrize("metric,d,M,efc", [(bind.L2, 20, 6, 40), (bind.IP, 33, 9, 64), (bind.L2, 7, 4, 30)])
 def test_differential_vs_reference(orc, ref, tmp_path, metric, d, M, efc):
     if ref is None:
@@ -126,6 +156,28 @@ def test_differential_vs_reference(orc, ref, tmp_path, metric, d, M, efc):
     fb.add(X)
     ra, rb = fa.search(Q, 25), fb.search(Q, 25)
     assert np.array_equal(ra["labels"], rb["labels"]) and np.array_equal(ra["dists"], rb["dists"])
+    # updates and replace_deleted against the live reference (same calls on both, files byte-identical)
+    rng = np.random.default_rng(11)
+    upd = rng.choice(1500, 150, replace=False).astype(np.uint64)
+    Xn = gauss(12, 150, d)
+    a.add(Xn, upd)
+    b.add(Xn, upd)
+    a.save(pa)
+    b.save(pb)
+    assert _sha(pa) == _sha(pb)
+    a2 = ref.hnsw_new(metric, d, 1500, M, efc, allow_replace_deleted=True)
+    b2 = orc.hnsw_new(metric, d, 1500, M, efc, allow_replace_deleted=True)
+    a2.add(X)
+    b2.add(X)
+    for l in rng.choice(1500, 100, replace=False).tolist():
+        a2.mark_delete(l)
+        b2.mark_delete(l)
+    nl = np.arange(50_000, 50_100, dtype=np.uint64)
+    a2.add_replace_deleted(gauss(13, 100, d), nl)
+    b2.add_replace_deleted(gauss(13, 100, d), nl)
+    a2.save(pa)
+    b2.save(pb)
+    assert _sha(pa) == _sha(pb)
     fa.remove(3)
     fb.remove(3)
     fa.save(str(tmp_path / "fa.bin"))
