@@ -8,9 +8,13 @@ batches of 10 000 queries, k=10; ef = the smallest value of the sweep whose reca
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm  (CUDA kernels through the C ABI)
   python bench.py --impl reference ...                           reference arm (unmodified hnswlib on host cores)
 
-N > 1 (torchrun, one rank per GPU): the data set is sharded, one 1M-point sub-index per GPU (weak scaling), every
-rank searches the same query batch, per-shard top-k are exchanged with an NCCL all_gather and merged on the GPU
-(SURVEY.md 8(e)).  `value` counts shard-level searches (N x nq per step); merged queries/s is value / N.
+N > 1 (torchrun, one rank per GPU): the data set is sharded, one 1M-point sub-index per GPU (weak scaling: N x 1M
+points in total), every rank searches the same query batch, per-shard top-k are exchanged with an NCCL all_gather and
+merged on the GPU.  The unit of work that is fixed per GPU is one (query, shard) search, so at N > 1
+`value` is in "shard-searches/s" (N x nq per step) and `merged_qps` = value / N is the rate of merged answers over the
+whole N x 1M data set.  The reference arm at N searches the same N shards on the host cores (its own graphs, its own
+recall-driven ef) and reports the same unit.  The default N = 1 run also measures C4 (BruteforceSearch 1M x 768, tensor
+roofline) and C5 (GPU graph build, HBM roofline) into `config.c4` / `config.build`.
 """
 import argparse
 import json
@@ -194,6 +198,22 @@ def cpu_reference_leg(a, path, batches, ef, budget_s, threads):
                        % (i, a.nq, ef, level, threads)), idx
 
 
+def merge_rows_numpy(L, D, k):
+    """k smallest (dist, label) pairs per row of [nq][shards*k] candidates (the merge kernel's contract), vectorised"""
+    order = np.lexsort((L, D), axis=1)[:, :k]
+    return np.take_along_axis(L, order, 1), np.take_along_axis(D, order, 1)
+
+
+def reference_exact_topk(a, X, labels, Q, threads):
+    """exact top-k of one shard by the UNMODIFIED reference's BruteforceSearch (as shipped, SSE)"""
+    from oracle import bind
+    ref = bind.Ref("sse")
+    bf = ref.bf_new(ref_metric(a), a.dim, X.shape[0])
+    bf.add(X, labels)
+    r = bf.search(Q, a.k, threads=threads)
+    return r["labels"], r["dists"]
+
+
 def pick_ef(a, search_fn, gt1000, Qs):
     if a.ef:
         r = search_fn(Qs, a.ef)
@@ -209,7 +229,93 @@ def pick_ef(a, search_fn, gt1000, Qs):
     return EF_SWEEP[-1], rec, table
 
 
+def c4_leg(pkg, local_rank, steps, warmup):
+    """BASELINE.json configs[3] (C4): BruteforceSearch exact k=100 on 1M x 768 inner product -- tcgen05 GEMM candidates
+    + exact re-rank (csrc/bf_tensor.cu), 10 000 queries per batch; tensor roofline F = 2*nq*N*d against the measured
+    bf16 peak; ids / distances compared with the unmodified reference (as shipped, SSE) on a query sample."""
+    import torch
+    from research_new_hnsw_b200.synth import lowrank_data
+    n, d, k, nq = 1_000_000, 768, 100, 10_000
+    X = lowrank_data(n, d, seed=11, latent=64, noise=0.1, normalize=True)
+    Qs = [lowrank_data(nq, d, seed=12 + b, latent=64, noise=0.1, normalize=True) for b in range(2)]
+    g = pkg.BruteforceSearch(pkg.InnerProductSpace(d), n, device=local_rank)
+    g.addPoints(X)
+    dev = torch.device("cuda", local_rank)
+    dQ = [torch.from_numpy(q).to(dev) for q in Qs]
+    ol = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for s in range(warmup):
+        g.searchKnnDevice(dQ[s % 2].data_ptr(), nq, k, ol.data_ptr(), od.data_ptr(), 0, stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        g.searchKnnDevice(dQ[s % 2].data_ptr(), nq, k, ol.data_ptr(), od.data_ptr(), 0, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    path_taken = {0: "scan", 1: "tensor", 2: "stream"}.get(g.stats()["hops_base"], "?")
+    hq = [torch.from_numpy(q).pin_memory() for q in Qs]
+    for s in range(2):
+        g.searchKnnBatch(hq[s % 2].numpy(), k)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        r = g.searchKnnBatch(hq[s % 2].numpy(), k)
+    e2e = (time.perf_counter() - t0) / steps
+    Qlast = Qs[(steps - 1) % 2]
+    small = []
+    for nq_s in (1, 8, 128):  # the bandwidth-bound regime: one pass over the fp32 rows is the floor
+        for _ in range(2):
+            g.searchKnnDevice(dQ[0].data_ptr(), nq_s, k, ol.data_ptr(), od.data_ptr(), 0, stream)
+        torch.cuda.synchronize()
+        e0.record()
+        for it in range(5):
+            g.searchKnnDevice(dQ[it % 2].data_ptr(), nq_s, k, ol.data_ptr(), od.data_ptr(), 0, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_s = e0.elapsed_time(e1) / 5
+        small.append({"nq": nq_s, "ms": round(ms_s, 4), "qps": round(nq_s / (ms_s * 1e-3), 1),
+                      "path": {0: "scan", 1: "tensor", 2: "stream"}.get(g.stats()["hops_base"], "?"),
+                      "hbm_frac_one_pass": round(4.0 * n * d / (ms_s * 1e-3) / 1e9 / peaks()[0], 3)})
+    cpu, exact = None, None
+    try:
+        from oracle import bind
+        T = os.cpu_count() or 1
+        b = bind.Ref("sse").bf_new(bind.IP, d, n)
+        b.add(X)
+        rr = b.search(Qlast[:64], k, threads=T)
+        exact = {"queries": 64, "ids_bit_exact": bool(np.array_equal(rr["labels"], r["labels"][:64])),
+                 "dists_bit_identical": bool(np.array_equal(rr["dists"], r["dists"][:64]))}
+        del b
+        lvl = bind.best_ref_level()
+        b = bind.Ref(lvl).bf_new(bind.IP, d, n)
+        b.add(X)
+        rb = b.search(Qlast[:128], k, threads=T)
+        cpu = {"value": 128 / rb["seconds"], "unit": "queries/s", "cores": T, "kind": "reference",
+               "sample": "128 queries, BruteforceSearch::searchKnn over %d threads, -O3 %s build of the unmodified headers"
+                         % (T, lvl)}
+    except Exception as e:  # the checker binary is missing: report it, never substitute
+        cpu = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+    pj = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_t = float(json.load(open(pj))["bf16_tflops"]) if os.path.exists(pj) else 1590.0
+    flops = 2.0 * nq * n * d
+    return {"workload": "C4: BruteforceSearch exact k=%d, %dx%d unit-norm rank-64+noise rows, inner product, %d queries "
+                        "per batch" % (k, n, d, nq),
+            "qps": nq / (ms * 1e-3), "ms_per_step": ms, "path": path_taken,
+            "e2e": {"value": nq / e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
+                    "d2h_bytes_per_step": nq * k * 12 + nq * 4, "api": "b200bf_search_batch (host pointers, pinned)"},
+            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak_t, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / peak_t, "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if os.path.exists(pj) else "fallback",
+                         "note": "algorithmic 2*nq*N*d over the WHOLE pipeline (candidate GEMM + exact fp32 re-rank)"},
+            "small_batches": small, "parity_vs_reference": exact, "cpu_baseline": cpu}
+
+
 def run_reference(a, rank, world):
+    """The unmodified reference on the host cores, same workload and unit as our arm: at N = 1 one 1M-point index; at
+    N > 1 the same N shards (seeds of shard_data) built by its own multi-threaded addPoint, every query searched on
+    every shard (T threads looping searchKnn, the hnsw_service pattern) and the per-shard top-k merged on the CPU."""
     if rank != 0:
         return
     from oracle import bind
@@ -219,42 +325,66 @@ def run_reference(a, rank, world):
               flush=True)
         return
     threads = os.cpu_count() or 1
-    X = shard_data(a, 0)
     batches = query_batches(a)
-    path, build_s = build_graph_with_reference(a, 0, X, threads)
-    ref = bind.Ref(bind.best_ref_level())
-    bf = ref.bf_new(ref_metric(a), a.dim, a.n)
-    bf.add(X)
     Qs = batches[0][:1000]
-    gt = bf.search(Qs, a.k, threads=threads)["labels"]
-    del bf
-    idx = ref.hnsw_load(ref_metric(a), a.dim, path)
-    ef, rec, table = pick_ef(a, lambda Q, e: idx.search(Q, a.k, e, threads=threads)["labels"], gt, Qs)
+    ref = bind.Ref(bind.best_ref_level())
+    budget = float(os.environ.get("B200HNSW_REF_BUILD_BUDGET_S", "480"))
+    shards, gts, build_s, build_note = [], [], 0.0, []
+    for r in range(world):
+        X = shard_data(a, r)
+        labels = np.arange(a.n, dtype=np.uint64) + np.uint64(r * a.n)
+        path, sec = build_graph_with_reference(a, r, X, threads)
+        build_s += sec
+        build_note.append(sec)
+        bf = ref.bf_new(ref_metric(a), a.dim, a.n)
+        bf.add(X, labels)
+        g = bf.search(Qs, a.k, threads=threads)
+        gts.append((g["labels"], g["dists"]))
+        del bf, X
+        shards.append(ref.hnsw_load(ref_metric(a), a.dim, path))
+        if r + 1 < world and build_s > 0 and build_s / (r + 1) * world > budget:
+            break  # a box too slow to build all N shards in time: measure what was built and say so
+    S = len(shards)
+    gt, _ = merge_rows_numpy(np.concatenate([g[0] for g in gts], 1), np.concatenate([g[1] for g in gts], 1), a.k)
+
+    def search(Q, ef):
+        rs = [idx.search(Q, a.k, ef, threads=threads) for idx in shards]
+        sec = sum(r["seconds"] for r in rs)
+        if S == 1:
+            return rs[0]["labels"], sec
+        t0 = time.perf_counter()
+        L, _ = merge_rows_numpy(np.concatenate([r["labels"] for r in rs], 1), np.concatenate([r["dists"] for r in rs], 1), a.k)
+        return L, sec + time.perf_counter() - t0
+
+    ef, rec, table = pick_ef(a, lambda Q, e: search(Q, e)[0], gt, Qs)
     ef_table = []
-    for e in (16, 32, 48, 64, 96, 128, 192, 256):
-        r_e = idx.search(batches[0][:2000], a.k, e, threads=threads)
-        ef_table.append({"ef": e, "recall_at_10": round(recall_at_k(r_e["labels"][:1000], gt), 4),
-                         "qps": 2000 / r_e["seconds"]})
+    if S == 1:
+        for e in (16, 32, 48, 64, 96, 128, 192, 256):
+            L, sec = search(batches[0][:2000], e)
+            ef_table.append({"ef": e, "recall_at_10": round(recall_at_k(L[:1000], gt), 4), "qps": 2000 / sec})
     for _ in range(a.warmup):
-        idx.search(batches[0][:2000], a.k, ef, threads=threads)
+        search(batches[0][:2000], ef)
     sec = 0.0
     # each step = a bounded sample of the batch so the whole run stays within minutes even on few cores
-    sample = min(a.nq, 10_000)
+    sample = min(a.nq, 10_000 if S == 1 else max(1000, 10_000 // S))
     for s in range(a.steps):
-        sec += idx.search(batches[s % len(batches)][:sample], a.k, ef, threads=threads)["seconds"]
-    qps = a.steps * sample / sec
-    line = {"impl": "reference", "metric": metric_name(a), "value": qps, "unit": "queries/s",
+        sec += search(batches[s % len(batches)][:sample], ef)[1]
+    rate = S * a.steps * sample / sec
+    unit = "queries/s" if world == 1 else "shard-searches/s"
+    line = {"impl": "reference", "metric": metric_name(a), "value": rate, "unit": unit,
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sec / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "merged_qps": rate / S, "total_points": S * a.n, "same_workload": S == world,
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
-                       "ef_table": ef_table,
+                       "ef_table": ef_table, "shards": S,
                        "graph": "built by the reference (addPoint, %d threads)%s" %
-                                (threads, "" if build_s == 0 else " in %.1f s = %.0f points/s" % (build_s, a.n / build_s)),
-                       "step": "%d queries of the batch" % sample},
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
+                                (threads, "" if build_s == 0 else " in %.1f s = %.0f points/s" % (build_s, S * a.n / build_s)),
+                       "step": "%d queries of the batch%s" % (sample, "" if S == 1 else
+                               ", each searched on all %d shards (%d threads per shard pass) + numpy top-k merge" % (S, threads))},
+            "cpu_baseline": {"value": rate, "unit": unit, "cores": threads, "kind": "reference",
                              "sample": "%d queries per step, ef=%d, -O3 %s build of the unmodified headers"
                                        % (sample, ef, bind.best_ref_level())},
-            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -321,6 +451,26 @@ def run_b200(a, rank, local_rank, world):
     gt_d = torch.from_numpy(g["dists"]).to(dev)
     gt_l, _ = merged(gt_l, gt_d, len(Qs))
     gt = gt_l.cpu().numpy().view(np.uint64)
+    # The ground truth must not rest on our own kernels alone: the UNMODIFIED reference's BruteforceSearch computes the
+    # exact top-k of this rank's shard for a query sample, the per-shard rows are gathered and merged with numpy.
+    gt_check = "oracle/_ref missing: ground truth is the exact-scan kernel's only"
+    try:
+        rl, rd = reference_exact_topk(a, X, shard_labels, Qs[:200], threads)
+        if sw > 1:
+            tl = torch.from_numpy(rl.view(np.int64)).to(dev)
+            td = torch.from_numpy(rd).to(dev)
+            al = torch.empty((sw,) + tuple(tl.shape), dtype=tl.dtype, device=dev)
+            ad = torch.empty((sw,) + tuple(td.shape), dtype=td.dtype, device=dev)
+            dist.all_gather_into_tensor(al, tl)
+            dist.all_gather_into_tensor(ad, td)
+            rl, rd = merge_rows_numpy(al.permute(1, 0, 2).reshape(200, -1).cpu().numpy().view(np.uint64),
+                                      ad.permute(1, 0, 2).reshape(200, -1).cpu().numpy(), a.k)
+        if not np.array_equal(rl, gt[:200]):
+            raise AssertionError("exact-scan ground truth differs from the reference BruteforceSearch")
+        gt_check = "exact-scan kernel%s; first 200 queries identical to the reference BruteforceSearch%s" % (
+            " + merge kernel" if sw > 1 else "", " per shard + numpy merge" if sw > 1 else "")
+    except (OSError, FileNotFoundError):
+        pass
 
     from research_new_hnsw_b200.sharded import PackedShardExchange
     packed = PackedShardExchange(a.nq, a.k, dev) if sw > 1 else None
@@ -351,6 +501,27 @@ def run_b200(a, rank, local_rank, world):
         ef = int(t.item())
 
     dbatches = [torch.from_numpy(b).to(dev) for b in batches]
+    merge_check = None
+    if sw > 1:
+        # N > 1 data path proven inline: the packed all_gather + merge kernel must return exactly the k best
+        # (dist, label) pairs of the per-shard rows, which are gathered separately and merged with numpy
+        ml, md = dev_search(dbatches[0], a.nq, ef)
+        torch.cuda.synchronize()
+        ml, md = ml.cpu().numpy().view(np.uint64).copy(), md.cpu().numpy().copy()
+        ol_ = torch.empty((a.nq, a.k), dtype=torch.int64, device=dev)
+        od_ = torch.empty((a.nq, a.k), dtype=torch.float32, device=dev)
+        idx.searchKnnDevice(dbatches[0].data_ptr(), a.nq, a.k, ef, ol_.data_ptr(), od_.data_ptr(), 0, 0, stream)
+        al = torch.empty((sw, a.nq, a.k), dtype=torch.int64, device=dev)
+        ad = torch.empty((sw, a.nq, a.k), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(al, ol_)
+        dist.all_gather_into_tensor(ad, od_)
+        el, ed = merge_rows_numpy(al.permute(1, 0, 2).reshape(a.nq, -1).cpu().numpy().view(np.uint64),
+                                  ad.permute(1, 0, 2).reshape(a.nq, -1).cpu().numpy(), a.k)
+        if not (np.array_equal(el, ml) and np.array_equal(ed, md)):
+            raise AssertionError("merged rows differ from the numpy merge of the gathered per-shard rows")
+        owners = np.bincount((ml[ml < np.uint64(sw * a.n)] // np.uint64(a.n)).astype(np.int64), minlength=sw)[:sw]
+        merge_check = {"rows_checked": int(a.nq), "equal_to_numpy_merge_of_gathered_shard_rows": True,
+                       "result_share_per_shard": [round(float(x) / ml.size, 4) for x in owners]}
     # counted work of every batch (outside the timed region; identical launches)
     works = []
     for dQ in dbatches:
@@ -509,26 +680,53 @@ def run_b200(a, rank, local_rank, world):
         gsec = time.perf_counter() - t0
         gst = gi.stats()
         rg = gi.searchKnnBatch(Qs, a.k, ef=ef)["labels"]
+        # roofline of the build: every distance evaluation the kernels counted (construction searches,
+        # heuristic pruning, reverse-link repair) x 4d bytes + the neighbour lists the construction searches read
+        b_alg = (gst["dist_evals"] * a.dim * 4 + gst["hops_base"] * (4 + 8 * a.M) + gst["hops_upper"] * (4 + 4 * a.M)
+                 + a.n * (a.dim * 4 + 8))
+        peak_b, peak_b_src = peaks()
         build_info = {"gpu_points_per_s": a.n / gsec, "gpu_seconds": gsec, "gpu_kernel_ms": gst["last_kernel_ms"],
+                      "kernel_launches": gst["kernel_launches"],
+                      "roofline": {"bound": "hbm", "achieved": b_alg / (gst["last_kernel_ms"] * 1e-3) / 1e9, "peak": peak_b,
+                                   "unit": "GB/s", "frac": b_alg / (gst["last_kernel_ms"] * 1e-3) / 1e9 / peak_b,
+                                   "frac_of_wall": b_alg / gsec / 1e9 / peak_b, "traffic": None,
+                                   "algorithmic_bytes": b_alg, "peak_source": peak_b_src,
+                                   "note": "counted: dist_evals*4d + list reads + one write of every row; time = CUDA "
+                                           "events around all build launches (gpu_kernel_ms); frac_of_wall uses the "
+                                           "wall clock incl. H2D of the rows"},
                       "dist_evals_per_point": gst["dist_evals"] / a.n,
                       "recall_at_10_gpu_built_graph": round(recall_at_k(rg, gt), 4),
                       "recall_at_10_reference_built_graph": round(rec, 4), "ef": ef,
                       "reference_points_per_s": (a.n / build_s) if build_s else None, "reference_threads": threads}
         del gi
     del X
+    c4 = None
+    if rank == 0 and world == 1 and a.metric == "l2" and not os.environ.get("B200HNSW_BENCH_SKIP_C4"):
+        del idx  # C4 needs 3 GB of rows + 1.5 GB bf16 copy; nothing else below touches the HNSW index
+        idx = None
+        try:
+            c4 = c4_leg(pkg, local_rank, max(3, min(a.steps, 10)), 3)
+        except Exception as e:
+            c4 = {"error": str(e)}
 
     if rank == 0:
         bytes_sum = [algorithmic_bytes(a, w, ef) for w in works]
         per_launch = float(np.mean([b[0] for b in bytes_sum]))
         peak, peak_src = peaks()
         achieved = per_launch / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        # dram__bytes_read+write of ONE launch from an `ncu --set full` capture (profiles/): only quoted when the
+        # capture was taken on this very configuration (same ef, 1 GPU, f32 rows); never measured inside this run
+        traffic, traffic_src = None, "none for this configuration (ncu capture is keyed by ef / storage / n_gpus)"
         tp = os.path.join(ROOT, "profiles", "search_kernel_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                for ent in tj.get("captures", []):
+                    if ent.get("ef") == ef and ent.get("n_gpus", 1) == world and ent.get("storage", "f32") == a.storage \
+                            and ent.get("metric", "l2") == a.metric and ent.get("n", 1_000_000) == a.n:
+                        traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source", tp)
             except Exception:
-                traffic = None
+                pass
         resets = int(sum(w[:, 3].sum() for w in works))
         cpu_leg = None  # measured on rank 0 at N = 1 only
         if world == 1:
@@ -539,7 +737,10 @@ def run_b200(a, rank, local_rank, world):
                            "sample": "unavailable: %s" % e}
         line = {
             "metric": metric_name(a), "value": world * a.nq * a.steps / (ms_total * 1e-3),
-            "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "unit": "queries/s" if (world == 1 or replica) else "shard-searches/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup,
+            "merged_qps": (world if replica else 1) * a.nq * a.steps / (ms_total * 1e-3),
+            "total_points": a.n * (1 if replica else world),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if a.storage == "f32" else "f32 accumulate over bf16 rows, f32 re-rank", "data": "synthetic",
             "config": {"workload": workload_name(a), "ef": ef, "recall_at_10": round(rec, 4), "recall_sweep": table,
@@ -547,15 +748,20 @@ def run_b200(a, rank, local_rank, world):
                        "parallelism": "1 GPU" if world == 1 else
                        ("replica%d: the same %d-point index on every GPU, each GPU serves its own query batches, no "
                         "data-path collective" % (world, a.n)) if replica else
-                       "shard%d: one %d-point sub-index per GPU, queries replicated, ONE packed NCCL all_gather + GPU merge "
-                       "per batch%s; value counts shard-level searches (merged queries/s = value/%d)"
-                       % (world, a.n, ", exchange of batch i overlapped with the search of batch i+1" if pipe else "", world),
+                       "shard%d: one %d-point sub-index per GPU (%d points in total), queries replicated, ONE packed NCCL "
+                       "all_gather + GPU merge per batch%s; value counts (query, shard) searches, merged_qps = value/%d is the "
+                       "rate of merged answers over the whole data set; ef is the smallest whose MERGED recall reaches the "
+                       "target, so it falls as N grows (each shard owes only its share of the global top-k)"
+                       % (world, a.n, world * a.n, ", exchange of batch i overlapped with the search of batch i+1" if pipe else "",
+                          world),
+                       "ground_truth": gt_check, "merge_check": merge_check,
                        "l2_policy": "inputs larger than L2 (index %.0f MB vs 126 MB L2); %d distinct query batches cycled"
                                     % ((a.n * (a.dim * 4 + 8 * a.M)) / 1e6, len(batches)),
-                       "graph": graph_note, "build": build_info,
+                       "graph": graph_note, "build": build_info, "c4": c4,
                        "visited_table_rebuilds_per_batch": resets / len(works)},
             "clocks": clocks, "per_rank": rank_diag,
-            "e2e": {"value": world * a.nq * a.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": world * a.nq * a.steps / e2e_s,
+                    "unit": "queries/s" if (world == 1 or replica) else "shard-searches/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
                     "api": "b200hnsw_search_batch (host pointers, pinned)" if sw == 1 else
                            "PipelinedShardSearch.submit_host: pinned H2D, b200hnsw_search_batch_device, packed NCCL "
@@ -563,7 +769,7 @@ def run_b200(a, rank, local_rank, world):
                            "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},
             "gpu_launches": a.steps * (1 if sw == 1 else 2),  # search kernel (+ merge kernel at N > 1)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "hnsw_search_kernel<team %d, %s>" % (64 if a.nq >= 2368 else 128, a.metric), "kernel_ms": kernel_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "hnsw_search_kernel<team %d, %s>" % (64 if a.nq >= 2368 else 128, a.metric), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": per_launch, "peak_source": peak_src,
                          "per_query": {"D": bytes_sum[0][1] / a.nq, "H0": bytes_sum[0][2] / a.nq,
                                        "Hup": bytes_sum[0][3] / a.nq}},

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200HNSW_ABI_VERSION 1
+#define B200HNSW_ABI_VERSION 2
 
 typedef enum {
     B200HNSW_OK = 0,
@@ -83,6 +83,9 @@ typedef struct {
     uint64_t visited_resets; /* times a per-query visited table was rebuilt (re-evaluations possible, results unchanged) */
     uint64_t kernel_launches;
     double last_kernel_ms;   /* CUDA-event time of the dominant kernel of the last call */
+    uint64_t dropped_reverse_edges; /* build: reverse edges not offered to a neighbour because more than 32 new points
+                                       of ONE batch selected it (the reference would have re-pruned it once per edge,
+                                       hnswalg.h:590-612); 0 on every configuration measured so far */
 } b200hnsw_stats;
 
 const char *b200hnsw_last_error(void);

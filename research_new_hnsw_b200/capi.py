@@ -43,7 +43,8 @@ class _Info(C.Structure):
 
 class _Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("queries", "dist_evals", "hops_base", "hops_upper", "visited_resets",
-                                          "kernel_launches")] + [("last_kernel_ms", C.c_double)]
+                                          "kernel_launches")] + [("last_kernel_ms", C.c_double),
+                                                                 ("dropped_reverse_edges", C.c_uint64)]
 
 
 EXPORTS = [

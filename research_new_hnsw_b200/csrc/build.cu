@@ -19,336 +19,19 @@
 // atomicAdd per edge and records each touched list once; build_reverse_kernel then gives every touched list to one
 // CTA which appends while there is room (:586-588) and otherwise re-runs the heuristic over existing + incoming
 // (:590-612), once per batch instead of once per edge.
+//
+// No host round trip inside flush(): batch boundaries depend only on the element levels, so the whole plan (list
+// slots of every batch) is computed up front and uploaded ONCE; per batch the host only enqueues three kernels and
+// a 4-byte memset.  build_reverse_kernel is persistent (grid-stride over the device-side count of touched lists).
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 #include <vector>
 
-#include "hnsw_index.cuh"
+#include "build_kernels.cuh"
 
 namespace b200 {
-
-constexpr int kTeam = 128;      // threads per CTA of the build kernels
-constexpr uint32_t kCapIn = 32;  // incoming reverse edges kept per list and batch
-
-struct BuildArgs {
-    float4 *vec;
-    uint32_t *links0, *up_base, *links_up;
-    const int32_t *plevel;     // [n] element levels
-    uint64_t *cand;            // [lists][efc] sorted keys
-    uint32_t *cand_cnt;        // [lists]
-    const uint32_t *list_off;  // [batch] slot of the point's level-0 list; level l at slot + l
-    const uint32_t *list_point, *list_level;  // [lists]
-    uint32_t *incnt;           // [cap + up_lists_cap]
-    uint64_t *incoming;        // [cap + up_lists_cap][kCapIn]
-    uint32_t *aff_node, *aff_level, *aff_count;
-    unsigned long long *work;  // [4] D, H0, Hup, resets (atomicAdd)
-    uint32_t cap, first, batch, lists;
-    uint32_t entry;
-    int32_t maxlevel;
-    uint32_t d4, maxM, maxM0, M, efc, hash_bits;
-    // update mode only (kernels instantiated with UPD = true re-link EXISTING points: repairConnectionsForUpdate,
-    // hnswalg.h:1075-1139); kept at the end so the insert-mode kernels see the layout they were tuned with
-    const uint32_t *batch_ids;  // [batch] ids of the points of this batch (insert mode: first + b)
-};
-
-template <int LPV, int CPL>
-__device__ __forceinline__ void load_row(float4 (&v)[CPL], const float4 *row, uint32_t d4, int sub) {
-#pragma unroll
-    for (int c = 0; c < CPL; c++) {
-        const uint32_t idx = sub + c * LPV;
-        v[c] = idx < d4 ? __ldg(row + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-}
-
-// Construction search for one new point: CTA b handles point first + b on all of its levels.
-template <int LPV, int CPL, int METRIC, bool UPD>
-__global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
-    const SearchSmem L(p.efc, list_cap, p.d4, p.hash_bits);
-    __shared__ int s_ints[kTeamInts];
-    TeamCtx c;
-    c.bind(smem, L, s_ints, p.hash_bits);
-    GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
-
-    const int tid = threadIdx.x;
-    const int sub = tid % LPV, grp = tid / LPV;
-    const uint32_t pid = UPD ? p.batch_ids[blockIdx.x] : p.first + blockIdx.x;
-    const uint32_t HS = 1u << p.hash_bits;
-    const int plevel = p.plevel[pid];
-
-    float4 q[CPL];
-    load_row<LPV, CPL>(q, p.vec + (size_t)pid * p.d4, p.d4, sub);
-    if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; *c.s_next = 0; c.ids[0] = p.entry; }
-    __syncthreads();
-    WorkCounters w;
-    uint32_t cur = p.entry;
-    eval_list<kTeam, LPV, CPL, METRIC>(q, g.vec, p.d4, c.ids, 1, c.dist, grp, sub);
-    __syncthreads();
-    float curdist = c.dist[0];
-    w.D += 1;
-    for (int level = p.maxlevel; level > plevel; --level) greedy_level<kTeam, LPV, CPL, METRIC>(c, q, g, level, cur, curdist, w);
-    const uint32_t slot0 = p.list_off[blockIdx.x];
-    for (int level = min(plevel, p.maxlevel); level >= 0; --level) {
-        __syncthreads();
-        for (uint32_t i = tid; i < HS; i += kTeam) c.hash[i] = kEmpty;
-        __syncthreads();
-        int cb, size;
-        beam_level<kTeam, LPV, CPL, METRIC>(c, q, g, level, p.efc, cur, curdist, cb, size, w);
-        const uint64_t *res = cb ? c.buf_b : c.buf_a;
-        uint64_t *out = p.cand + (size_t)(slot0 + level) * p.efc;
-        for (int j = tid; j < size; j += kTeam) out[j] = res[j] & kKeyMask;
-        if (tid == 0) p.cand_cnt[slot0 + level] = (uint32_t)size;
-        // next level starts from the closest candidate (= selectedNeighbors.back(), hnswalg.h:524,629: the closest
-        // candidate always survives the heuristic)
-        cur = (uint32_t)res[0] & kIdMask;
-        curdist = ord2f((uint32_t)(res[0] >> 32));
-    }
-    if (tid == 0) {
-        atomicAdd(p.work + 0, (unsigned long long)w.D); atomicAdd(p.work + 1, (unsigned long long)w.H0);
-        atomicAdd(p.work + 2, (unsigned long long)w.Hup); atomicAdd(p.work + 3, (unsigned long long)w.resets);
-    }
-}
-
-// getNeighborsByHeuristic2 (hnswalg.h:443-483) for one candidate list sorted closest-first: accept c iff every already
-// accepted r has dist(r, c) >= dist(base, c); stop at Mlimit.  Selected keys end up in sel[0..ns), their ids in ids[].
-// The candidate's vector is register-resident and the next candidate's is prefetched while the current one is
-// compared against the accepted set (whose rows are re-read through L1/L2).
-template <int LPV, int CPL, int METRIC>
-__device__ __forceinline__ int heuristic_prune(const GraphView &g, const uint64_t *cand, int n, int Mlimit,
-                                               uint64_t *sel, uint32_t *ids, float *dist, uint32_t &evals) {
-    const int tid = threadIdx.x;
-    const int sub = tid % LPV, grp = tid / LPV;
-    if (n < Mlimit) {  // hnswalg.h:446-448
-        for (int j = tid; j < n; j += kTeam) { sel[j] = cand[j]; ids[j] = (uint32_t)cand[j] & kIdMask; }
-        __syncthreads();
-        return n;
-    }
-    int ns = 0;
-    float4 v[CPL], vn[CPL];
-    load_row<LPV, CPL>(v, g.vec + (size_t)((uint32_t)cand[0] & kIdMask) * g.d4, g.d4, sub);
-    for (int ci = 0; ci < n && ns < Mlimit; ci++) {
-        const uint64_t key = cand[ci];
-        const float dq = ord2f((uint32_t)(key >> 32));
-        if (ci + 1 < n) load_row<LPV, CPL>(vn, g.vec + (size_t)((uint32_t)cand[ci + 1] & kIdMask) * g.d4, g.d4, sub);
-        eval_list<kTeam, LPV, CPL, METRIC, true>(v, g.vec, g.d4, ids, ns, dist, grp, sub);
-        evals += ns;
-        __syncthreads();
-        bool bad = false;
-        for (int j = tid; j < ns; j += kTeam) bad |= dist[j] < dq;
-        bad = __syncthreads_or(bad);
-        if (!bad) {
-            if (tid == 0) { sel[ns] = key; ids[ns] = (uint32_t)key & kIdMask; }
-            ns++;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int cc = 0; cc < CPL; cc++) v[cc] = vn[cc];
-    }
-    return ns;
-}
-
-struct LinkSmem {
-    uint32_t off_sel, off_raw, off_srt, off_ids, off_dist, total;
-    __host__ __device__ explicit LinkSmem(uint32_t cap) {
-        uint32_t o = 0;
-        off_sel = o; o += cap * 8;
-        off_raw = o; o += cap * 8;
-        off_srt = o; o += cap * 8;
-        off_ids = o; o += cap * 4;
-        off_dist = o; o += cap * 4;
-        total = o;
-    }
-};
-
-__device__ __forceinline__ uint32_t list_id(const BuildArgs &p, uint32_t node, uint32_t level) {
-    return level == 0 ? node : p.cap + p.up_base[node] + level - 1;
-}
-__device__ __forceinline__ uint32_t *list_ptr(const BuildArgs &p, uint32_t node, uint32_t level) {
-    return level == 0 ? p.links0 + (size_t)node * p.maxM0
-                      : p.links_up + ((size_t)p.up_base[node] + level - 1) * p.maxM;
-}
-
-// One CTA per (new point, level): prune the candidates to M, write the forward list, stage the reverse edges.
-template <int LPV, int CPL, int METRIC, bool UPD>
-__global__ void __launch_bounds__(kTeam) build_link_kernel(const BuildArgs p) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t capc = max(p.maxM0, p.maxM) + kCapIn;
-    const LinkSmem L(capc);
-    uint64_t *sel = (uint64_t *)(smem + L.off_sel);
-    uint32_t *ids = (uint32_t *)(smem + L.off_ids);
-    float *dist = (float *)(smem + L.off_dist);
-    GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
-    const int tid = threadIdx.x;
-    const uint32_t slot = blockIdx.x;
-    const uint32_t pid = p.list_point[slot], level = p.list_level[slot];
-    int n = (int)p.cand_cnt[slot];
-    uint64_t *cand = p.cand + (size_t)slot * p.efc;
-    if constexpr (UPD) {
-        // the point is already in the graph, so its own search finds it: drop it from the candidates
-        // (filteredTopCandidates, hnswalg.h:1117-1123) by closing the gap in the sorted list
-        __shared__ int s_self;
-        if (tid == 0) s_self = n;
-        __syncthreads();
-        for (int j = tid; j < n; j += kTeam)
-            if (((uint32_t)cand[j] & kIdMask) == pid) s_self = j;
-        __syncthreads();
-        const int self = s_self;
-        if (self < n) {
-            for (int base = self; base < n - 1; base += kTeam) {
-                const int j = base + tid;
-                const uint64_t v = j < n - 1 ? cand[j + 1] : 0;
-                __syncthreads();
-                if (j < n - 1) cand[j] = v;
-                __syncthreads();
-            }
-            n--;
-        }
-        if (n == 0) return;  // nothing but the point itself on this level: its links stay (hnswalg.h:1127)
-    }
-    uint32_t evals = 0;
-    const int ns = heuristic_prune<LPV, CPL, METRIC>(g, cand, n, (int)p.M, sel, ids, dist, evals);
-    uint32_t *mine = list_ptr(p, pid, level);
-    if constexpr (UPD) {  // the old forward list is replaced, not extended
-        const int Mcur = (int)(level ? p.maxM : p.maxM0);
-        for (int j = ns + tid; j < Mcur; j += kTeam) mine[j] = kEmpty;
-    }
-    for (int j = tid; j < ns; j += kTeam) {
-        const uint32_t r = ids[j];
-        mine[j] = r;
-        const uint32_t lid = list_id(p, r, level);
-        const uint32_t s = atomicAdd(p.incnt + lid, 1u);
-        if (s == 0) {
-            const uint32_t pos = atomicAdd(p.aff_count, 1u);
-            p.aff_node[pos] = r;
-            p.aff_level[pos] = level;
-        }
-        if (s < kCapIn) p.incoming[(size_t)lid * kCapIn + s] = (sel[j] & 0xFFFFFFFF00000000ull) | pid;
-    }
-    if (tid == 0) atomicAdd(p.work + 0, (unsigned long long)evals);
-}
-
-// One CTA per touched list: append the incoming new points while there is room, otherwise re-run the heuristic over
-// existing + incoming neighbours (distances to this node) and rewrite the list.
-template <int LPV, int CPL, int METRIC, bool UPD>
-__global__ void __launch_bounds__(kTeam) build_reverse_kernel(const BuildArgs p, uint32_t n_aff) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const uint32_t capc = max(p.maxM0, p.maxM) + kCapIn;
-    const LinkSmem L(capc);
-    uint64_t *sel = (uint64_t *)(smem + L.off_sel);
-    uint64_t *raw = (uint64_t *)(smem + L.off_raw);
-    uint64_t *srt = (uint64_t *)(smem + L.off_srt);
-    uint32_t *ids = (uint32_t *)(smem + L.off_ids);
-    float *dist = (float *)(smem + L.off_dist);
-    GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
-    const int tid = threadIdx.x;
-    const int sub = tid % LPV, grp = tid / LPV;
-    if (blockIdx.x >= n_aff) return;
-    const uint32_t node = p.aff_node[blockIdx.x], level = p.aff_level[blockIdx.x];
-    const uint32_t lid = list_id(p, node, level);
-    int t = (int)min(p.incnt[lid], kCapIn);
-    const int Mcur = (int)(level ? p.maxM : p.maxM0);
-    uint32_t *lst = list_ptr(p, node, level);
-    int deg = 0;
-    for (int b0 = 0; b0 < Mcur; b0 += kTeam) {
-        uint32_t v = kEmpty;
-        if (b0 + tid < Mcur) { v = lst[b0 + tid]; ids[b0 + tid] = v; }
-        deg += __syncthreads_count(v != kEmpty);
-    }
-    for (int j = tid; j < t; j += kTeam) raw[deg + j] = p.incoming[(size_t)lid * kCapIn + j];
-    __syncthreads();
-    if (tid == 0) p.incnt[lid] = 0;  // ready for the next batch
-    if constexpr (UPD) {
-        // a re-linked point may already be a neighbour of this node (is_cur_c_present, hnswalg.h:566-580): keep the
-        // existing edge, drop the incoming duplicate
-        __shared__ int s_keep;
-        if (tid == 0) {
-            int keep = 0;
-            for (int j = 0; j < t; j++) {
-                const uint64_t key = raw[deg + j];
-                bool present = false;
-                for (int i = 0; i < deg; i++) present |= ids[i] == (uint32_t)key;
-                if (!present) raw[deg + keep++] = key;
-            }
-            s_keep = keep;
-        }
-        __syncthreads();
-        t = s_keep;
-        if (t == 0) return;
-    }
-    if (deg + t <= Mcur) {
-        // room for all (hnswalg.h:586-588); ordered by new id so the list does not depend on atomic arrival order
-        for (int j = tid; j < t; j += kTeam) {
-            const uint32_t id = (uint32_t)raw[deg + j];
-            int r = 0;
-            for (int i = 0; i < t; i++) r += ((uint32_t)raw[deg + i] < id) ? 1 : 0;
-            lst[deg + r] = id;
-        }
-        return;
-    }
-    // full: candidates = existing (distances to this node evaluated now, :597-601) + incoming
-    float4 q[CPL];
-    load_row<LPV, CPL>(q, p.vec + (size_t)node * p.d4, p.d4, sub);
-    eval_list<kTeam, LPV, CPL, METRIC>(q, g.vec, p.d4, ids, deg, dist, grp, sub);
-    __syncthreads();
-    for (int j = tid; j < deg; j += kTeam) raw[j] = make_key(dist[j], ids[j]);
-    __syncthreads();
-    const int n = deg + t;
-    for (int j = tid; j < n; j += kTeam) {  // rank sort, closest first
-        const uint64_t key = raw[j];
-        int r = 0;
-        for (int i = 0; i < n; i++) r += (raw[i] < key || (raw[i] == key && i < j)) ? 1 : 0;
-        srt[r] = key;
-    }
-    __syncthreads();
-    uint32_t evals = (uint32_t)deg;
-    const int ns = heuristic_prune<LPV, CPL, METRIC>(g, srt, n, Mcur, sel, ids, dist, evals);
-    for (int j = tid; j < Mcur; j += kTeam) lst[j] = j < ns ? ids[j] : kEmpty;
-    if (tid == 0) atomicAdd(p.work + 0, (unsigned long long)evals);
-}
-
-template <int LPV, int CPL, int METRIC, bool UPD>
-static int run_batch(const BuildArgs &a, size_t smem_search, size_t smem_link, uint32_t *h_aff, cudaStream_t st) {
-    static bool configured[16] = {};
-    int d = 0;
-    cudaGetDevice(&d);
-    if (d < 16 && !configured[d]) {
-        cudaFuncAttributes fa;
-        int optin = 0;
-        B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, build_search_kernel<LPV, CPL, METRIC, UPD>));
-        B200_CUDA_OK(cudaFuncSetAttribute(build_search_kernel<LPV, CPL, METRIC, UPD>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
-        configured[d] = true;
-    }
-    build_search_kernel<LPV, CPL, METRIC, UPD><<<a.batch, kTeam, smem_search, st>>>(a);
-    build_link_kernel<LPV, CPL, METRIC, UPD><<<a.lists, kTeam, smem_link, st>>>(a);
-    B200_CUDA_OK(cudaMemcpyAsync(h_aff, a.aff_count, 4, cudaMemcpyDeviceToHost, st));
-    B200_CUDA_OK(cudaStreamSynchronize(st));
-    const uint32_t n_aff = *h_aff;
-    if (n_aff) build_reverse_kernel<LPV, CPL, METRIC, UPD><<<n_aff, kTeam, smem_link, st>>>(a, n_aff);
-    B200_CUDA_OK(cudaMemsetAsync(a.aff_count, 0, 4, st));
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-template <int METRIC, bool UPD = false>
-static int run_batch_metric(const BuildArgs &a, size_t s1, size_t s2, uint32_t *h_aff, cudaStream_t st) {
-    const uint32_t d4 = a.d4;
-    if (d4 <= 8) return run_batch<8, 1, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 16) return run_batch<8, 2, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 24) return run_batch<8, 3, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 32) return run_batch<8, 4, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 48) return run_batch<16, 3, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 64) return run_batch<16, 4, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 96) return run_batch<32, 3, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 128) return run_batch<32, 4, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 192) return run_batch<32, 6, METRIC, UPD>(a, s1, s2, h_aff, st);
-    if (d4 <= 256) return run_batch<32, 8, METRIC, UPD>(a, s1, s2, h_aff, st);
-    set_error("dimension > 1024 is not supported by the build kernels");
-    return B200HNSW_E_UNSUPPORTED;
-}
 
 // ---- host side ---------------------------------------------------------------------------------------------
 
@@ -364,7 +47,7 @@ static size_t env_size(const char *name, size_t dflt) {
 int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted) {
     std::lock_guard<std::mutex> g(mu);
     HostImage &m = host;
-    std::vector<uint32_t> updates;
+    std::vector<uint32_t> updates, revived;  // revived: slots that were marked deleted until this call
     for (size_t i = 0; i < n; i++) {
         const uint64_t lab = labels ? labels[i] : (uint64_t)m.cur;
         auto known = m.label_lookup.find(lab);
@@ -379,6 +62,7 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
                 *((unsigned char *)m.rec(c) + 2) &= (unsigned char)~1;  // unmarkDeletedInternal
                 m.num_deleted--;
                 flags_dirty = true;
+                if (c < linked) revived.push_back(c);
             }
             memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
             if (c < linked) updates.push_back(c);  // a staged point is simply linked with its new vector later
@@ -398,7 +82,7 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
             m.num_deleted--;
             flags_dirty = true;
             memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
-            if (c < linked) updates.push_back((uint32_t)c);
+            if (c < linked) { updates.push_back((uint32_t)c); revived.push_back((uint32_t)c); }
             continue;
         }
         if (m.cur >= m.max_elements) {
@@ -421,69 +105,124 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
             m.maxlevel = level;
         }
     }
-    return updates.empty() ? 0 : relink_points(std::move(updates));
+    return updates.empty() ? 0 : relink_points(std::move(updates), revived);
 }
 
-// updatePoint (hnswalg.h:995-1139) for points that are already part of the device graph, batched.  The new vector is
-// uploaded, then repairConnectionsForUpdate runs on the GPU with the construction kernels in update mode: search from the
-// entry point, the point itself dropped from its candidates, heuristic selection, forward list REPLACED, reverse edges
-// added unless already present (mutuallyConnectNewElement with isUpdate, :485-639).  The first phase of the reference --
-// re-pruning every old neighbour over the 1-hop/2-hop neighbourhood (:1009-1069) -- is NOT performed: old neighbours keep
-// their edge to the moved point.
-int HnswIndex::relink_points(std::vector<uint32_t> ids) {
+// updatePoint (hnswalg.h:995-1139) for points that are already part of the device graph.  Per group of points: the new
+// vectors (and labels: replace_deleted relabels) are staged and scattered into the device rows, the first phase
+// re-prunes every old neighbour over the 1-hop + 2-hop set (update_*_kernel, :1009-1069), then
+// repairConnectionsForUpdate runs with the construction kernels in update mode: search from the entry point, the point
+// itself dropped from its candidates, heuristic selection, forward list REPLACED, reverse edges added unless already
+// present (mutuallyConnectNewElement with isUpdate, :485-639).
+//
+// The reference updates one point at a time, each seeing the graph the previous update left.  Up to
+// B200HNSW_UPDATE_SEQ (default 2048) points per call are therefore processed ONE PER GROUP, in call order -- the same
+// sequence of graph states as the reference; larger calls are processed in groups that see the graph as of the start of
+// their group (the batching rule of the build), a neighbour shared by two points of a group being re-pruned for the
+// later one.
+int HnswIndex::relink_points(std::vector<uint32_t> ids, const std::vector<uint32_t> &revived) {
     HostImage &m = host;
-    std::sort(ids.begin(), ids.end());
-    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-    B200_CUDA_OK(cudaSetDevice(dev.device));
-    {   // new vectors -> padded device rows
-        std::vector<float> row(dev.d4 * 4, 0.f);
-        for (uint32_t id : ids) {
-            memcpy(row.data(), m.rec(id) + m.off_data, m.dim * 4);
-            B200_CUDA_OK(cudaMemcpy((float *)dev.vec + (size_t)id * dev.d4 * 4, row.data(), dev.d4 * 16, cudaMemcpyHostToDevice));
-            B200_CUDA_OK(cudaMemcpy(dev.labels + id, m.rec(id) + m.off_label, 8, cudaMemcpyHostToDevice));  // replace_deleted relabels
-            const int rc16 = sync_bf16(id, 1);
-            if (rc16) return rc16;
-        }
+    {   // call order, one entry per point (a label given twice: the host image already holds the last vector)
+        std::vector<uint32_t> uniq;
+        uniq.reserve(ids.size());
+        std::unordered_map<uint32_t, bool> seen;
+        for (uint32_t id : ids)
+            if (seen.emplace(id, true).second) uniq.push_back(id);
+        ids.swap(uniq);
     }
-    if (linked <= 1) return 0;  // a single element has nothing to connect to (hnswalg.h:1001-1003)
+    B200_CUDA_OK(cudaSetDevice(dev.device));
     const size_t build_ratio = env_size("B200HNSW_BUILD_RATIO", 32);
     const size_t max_batch = env_size("B200HNSW_BUILD_BATCH", 16384);
+    const size_t seq_limit = env_size("B200HNSW_UPDATE_SEQ", 2048);
+    const bool sequential = ids.size() <= seq_limit;
     if (!bld.plevel) B200_CUDA_OK(cudaMalloc(&bld.plevel, std::max<size_t>(dev.cap, 1) * 4));
     B200_CUDA_OK(cudaMemcpy(bld.plevel, m.levels.data(), linked * 4, cudaMemcpyHostToDevice));
+    // A slot that was marked deleted until this call holds its OLD vector on the device until its own turn: the
+    // kernels must keep seeing it as deleted until then (the reference unmarks it right before updatePoint, :983-986,
+    // :1168-1171).  The device marks start from that state; scatter_rows_kernel clears the mark with the new row.
+    revived_on_device = !revived.empty();
+    if (revived_on_device) {
+        const int rcf = upload_flags(nullptr, revived.data(), revived.size());
+        if (rcf) { revived_on_device = false; return rcf; }
+    }
     BuildArgs a{};
     size_t max_lists = 0, smem_search = 0, smem_link = 0;
     int rc = prepare_build(&a, max_batch, &max_lists, &smem_search, &smem_link);
+    revived_on_device = false;
     if (rc) return rc;
+    const bool nb = a.flags != nullptr;
     if (!bld.batch_ids) B200_CUDA_OK(cudaMalloc(&bld.batch_ids, max_batch * 4));
+    // scratch of the first phase: one re-pruned list per (list of the group, neighbour slot); bounded to 64 MB
+    const size_t per_list = m.maxM0 * m.maxM0 * 4;
+    const size_t upd_lists = std::max<size_t>(64, std::min<size_t>(max_lists, ((size_t)64 << 20) / per_list));
+    if (!bld.newlists || bld.newlists_cap < upd_lists) {
+        cudaFree(bld.newlists);
+        bld.newlists = nullptr;
+        B200_CUDA_OK(cudaMalloc(&bld.newlists, upd_lists * per_list));
+        bld.newlists_cap = upd_lists;
+    }
+    const size_t rowf = dev.d4 * 4;
+    const size_t stage_rows = sequential ? 1 : std::min(max_batch, ids.size());
+    if (bld.stage_cap < stage_rows) {
+        cudaFree(bld.stage_rows); cudaFree(bld.stage_labels);
+        bld.stage_rows = nullptr; bld.stage_labels = nullptr;
+        B200_CUDA_OK(cudaMalloc(&bld.stage_rows, stage_rows * rowf * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.stage_labels, stage_rows * 8));
+        bld.stage_cap = stage_rows;
+    }
     std::vector<uint32_t> off, lp, ll;
-    uint32_t h_aff = 0;
+    std::vector<float> hrows;
+    std::vector<uint64_t> hlabels;
     uint64_t launches = 0;
     for (size_t b0 = 0; b0 < ids.size() && rc == 0;) {
-        size_t B = std::max<size_t>(1, std::min(max_batch, linked / build_ratio));
+        size_t B = sequential ? 1 : std::max<size_t>(1, std::min(max_batch, linked / build_ratio));
         B = std::min(B, ids.size() - b0);
         off.clear(); lp.clear(); ll.clear();
         size_t used = 0;
         for (; used < B; used++) {
             const uint32_t id = ids[b0 + used];
             const int top = std::min(m.levels[id], dev_maxlevel);
-            if (lp.size() + (size_t)top + 1 > max_lists) break;
+            if (used > 0 && lp.size() + (size_t)top + 1 > std::min(max_lists, upd_lists)) break;
             off.push_back((uint32_t)lp.size());
             for (int l = 0; l <= top; l++) { lp.push_back(id); ll.push_back((uint32_t)l); }
         }
         B = used;
+        // new vectors / labels of the group -> device rows (one staged copy + one scatter launch per group)
+        hrows.assign(B * rowf, 0.f);
+        hlabels.resize(B);
+        for (size_t i = 0; i < B; i++) {
+            const uint32_t id = ids[b0 + i];
+            memcpy(hrows.data() + i * rowf, m.rec(id) + m.off_data, m.dim * 4);
+            memcpy(&hlabels[i], m.rec(id) + m.off_label, 8);
+        }
+        B200_CUDA_OK(cudaMemcpyAsync(bld.stage_rows, hrows.data(), B * rowf * 4, cudaMemcpyHostToDevice, stream));
+        B200_CUDA_OK(cudaMemcpyAsync(bld.stage_labels, hlabels.data(), B * 8, cudaMemcpyHostToDevice, stream));
         B200_CUDA_OK(cudaMemcpyAsync(bld.batch_ids, ids.data() + b0, B * 4, cudaMemcpyHostToDevice, stream));
+        scatter_rows_kernel<<<(unsigned)((B * 32 + 127) / 128), 128, 0, stream>>>(
+            (const float4 *)bld.stage_rows, bld.stage_labels, bld.batch_ids, (uint32_t)B, (uint32_t)dev.d4, (uint32_t)dev.d16,
+            dev.vec, dev.labels, prm.storage == B200HNSW_BF16 ? dev.vec16 : nullptr, nb ? dev.flags : nullptr);
+        launches += 1;
+        b0 += B;
+        if (linked <= 1) continue;  // a single element has nothing to connect to (hnswalg.h:1001-1003)
         B200_CUDA_OK(cudaMemcpyAsync(bld.list_off, off.data(), B * 4, cudaMemcpyHostToDevice, stream));
         B200_CUDA_OK(cudaMemcpyAsync(bld.list_point, lp.data(), lp.size() * 4, cudaMemcpyHostToDevice, stream));
         B200_CUDA_OK(cudaMemcpyAsync(bld.list_level, ll.data(), ll.size() * 4, cudaMemcpyHostToDevice, stream));
         a.first = 0; a.batch = (uint32_t)B; a.lists = (uint32_t)lp.size();
         a.entry = dev_entry; a.maxlevel = dev_maxlevel;
         a.batch_ids = bld.batch_ids;
-        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0, true>(a, smem_search, smem_link, &h_aff, stream)
-                                       : run_batch_metric<1, true>(a, smem_search, smem_link, &h_aff, stream);
-        launches += 3;
-        b0 += B;
+        rc = build_run_update_phase1(prm.metric, a, bld.newlists, stream);
+        if (rc) break;
+        rc = nb ? build_run_batch_update_nb(prm.metric, a, smem_search, smem_link, stream)
+                : build_run_batch_update(prm.metric, a, smem_search, smem_link, stream);
+        launches += 6;
     }
-    if (rc == 0) B200_CUDA_OK(cudaStreamSynchronize(stream));
+    {
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        if (rc == 0 && e != cudaSuccess) {
+            set_error(std::string("CUDA error in updatePoint: ") + cudaGetErrorString(e));
+            rc = B200HNSW_E_CUDA;
+        }
+    }
     stats.kernel_launches += launches;
     mirror_dirty = true;
     return rc;
@@ -556,10 +295,10 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
         B200_CUDA_OK(cudaMalloc(&bld.aff_level, max_lists * m.M * 4));
         B200_CUDA_OK(cudaMalloc(&bld.aff_count, 4));
         B200_CUDA_OK(cudaMemset(bld.aff_count, 0, 4));
-        B200_CUDA_OK(cudaMalloc(&bld.work, 32));
+        B200_CUDA_OK(cudaMalloc(&bld.work, 64));
         bld.cand_efc = m.efc;
     }
-    B200_CUDA_OK(cudaMemset(bld.work, 0, 32));
+    B200_CUDA_OK(cudaMemset(bld.work, 0, 64));
 
     const size_t list_cap = std::max(m.maxM, m.maxM0);
     BuildArgs &a = *(BuildArgs *)args;
@@ -570,15 +309,29 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
     a.aff_node = bld.aff_node; a.aff_level = bld.aff_level; a.aff_count = bld.aff_count; a.work = bld.work;
     a.cap = (uint32_t)dev.cap; a.d4 = (uint32_t)dev.d4; a.maxM = (uint32_t)m.maxM; a.maxM0 = (uint32_t)m.maxM0;
     a.M = (uint32_t)m.M; a.efc = (uint32_t)m.efc;
+    // elements marked deleted: the construction search keeps them out of the candidates (NB kernels, buffer of 2 * efc)
+    const bool nb = m.num_deleted != 0 || revived_on_device;
+    if (nb) {
+        if (linked >= (1u << 30)) {
+            set_error("build with deleted elements supports at most 2^30 elements");
+            return B200HNSW_E_UNSUPPORTED;
+        }
+        if (!revived_on_device) {  // relink_points has already uploaded the marks it wants the kernels to see
+            const int rcf = upload_flags();
+            if (rcf) return rcf;
+        }
+    }
+    a.flags = nb ? dev.flags : nullptr;
+    const size_t bufcap = nb ? 2 * m.efc : m.efc;
     // construction searches evaluate ~40 * efc nodes; a table of ~32 * efc slots is rebuilt about once in four searches
     // and lets twice as many CTAs share an SM as the no-rebuild size (measured: -30 % build time, same graph)
     {
         size_t want = std::min<size_t>(8192, 32 * m.efc + 1024);
-        want = std::max(want, 2 * (m.efc + list_cap));
+        want = std::max(want, 8 * (bufcap + list_cap) / 3 + 64);  // a hop must fit above the 5/8 rebuild mark
         a.hash_bits = 10;
         while ((1ull << a.hash_bits) < want) a.hash_bits++;
     }
-    const SearchSmem SL(a.efc, (uint32_t)list_cap, a.d4, a.hash_bits);
+    const SearchSmem SL((uint32_t)bufcap, (uint32_t)list_cap, a.d4, a.hash_bits);
     const LinkSmem LL((uint32_t)list_cap + kCapIn);
     if (SL.total > 226 * 1024) {
         set_error("ef_construction too large for the build kernel's shared memory");
@@ -664,69 +417,99 @@ int HnswIndex::flush() {
         if (rcp) return rcp;
     }
 
+    const bool nb = a.flags != nullptr;
+    // ---- the whole batch plan, from host-side information only (levels, number of linked points) ----
+    struct BatchPlan { uint32_t first, batch, lists_off, lists, entry; int32_t maxlevel; };
+    std::vector<BatchPlan> plan;
+    const size_t linked0 = linked;
+    std::vector<uint32_t> off_all(n_new), lp_all, ll_all;
+    lp_all.reserve(n_new + n_new / 8 + 16);
+    ll_all.reserve(n_new + n_new / 8 + 16);
+    {
+        size_t lk = linked;
+        uint32_t ent = dev_entry;
+        int ml = dev_maxlevel;
+        if (lk == 0) {  // first element: nothing to link (hnswalg.h:1255-1259)
+            ent = 0;
+            ml = m.levels[0];
+            lk = 1;
+        }
+        while (lk < m.cur) {
+            size_t B = std::max<size_t>(1, std::min(max_batch, lk / build_ratio));
+            B = std::min(B, m.cur - lk);
+            BatchPlan bp{(uint32_t)lk, 0, (uint32_t)lp_all.size(), 0, ent, ml};
+            size_t used = 0, nl = 0;
+            while (used < B) {
+                const int lev = m.levels[lk + used];
+                const int top = std::min(lev, ml);
+                if (used > 0 && nl + (size_t)top + 1 > max_lists) break;  // the candidate pool holds max_lists lists
+                off_all[lk + used - linked0] = (uint32_t)nl;
+                for (int l = 0; l <= top; l++) { lp_all.push_back((uint32_t)(lk + used)); ll_all.push_back((uint32_t)l); }
+                nl += (size_t)top + 1;
+                used++;
+                if (lev > ml) break;  // a new top level ends the batch: it is the entry point of everything after it
+            }
+            bp.batch = (uint32_t)used;
+            bp.lists = (uint32_t)nl;
+            plan.push_back(bp);
+            const size_t last = lk + used - 1;
+            if (m.levels[last] > ml) { ent = (uint32_t)last; ml = m.levels[last]; }
+            lk += used;
+        }
+    }
+    uint32_t *d_off = nullptr, *d_lp = nullptr, *d_ll = nullptr;
+    B200_CUDA_OK(cudaMalloc(&d_off, std::max<size_t>(n_new, 1) * 4));
+    B200_CUDA_OK(cudaMalloc(&d_lp, std::max<size_t>(lp_all.size(), 1) * 4));
+    B200_CUDA_OK(cudaMalloc(&d_ll, std::max<size_t>(ll_all.size(), 1) * 4));
+    B200_CUDA_OK(cudaMemcpyAsync(d_off, off_all.data(), n_new * 4, cudaMemcpyHostToDevice, stream));
+    B200_CUDA_OK(cudaMemcpyAsync(d_lp, lp_all.data(), lp_all.size() * 4, cudaMemcpyHostToDevice, stream));
+    B200_CUDA_OK(cudaMemcpyAsync(d_ll, ll_all.data(), ll_all.size() * 4, cudaMemcpyHostToDevice, stream));
+
     cudaEvent_t e0, e1;
     B200_CUDA_OK(cudaEventCreate(&e0));
     B200_CUDA_OK(cudaEventCreate(&e1));
     B200_CUDA_OK(cudaEventRecord(e0, stream));
-    std::vector<uint32_t> off, lp, ll;
-    uint32_t h_aff = 0;
     uint64_t launches = 0;
     int rc = 0;
-    while (linked < m.cur && rc == 0) {
-        if (linked == 0) {  // first element: nothing to link (hnswalg.h:1255-1259)
-            dev_entry = 0;
-            dev_maxlevel = m.levels[0];
-            linked = 1;
-            continue;
-        }
-        size_t B = std::max<size_t>(1, std::min(max_batch, linked / build_ratio));
-        B = std::min(B, m.cur - linked);
-        for (size_t j = 0; j < B; j++)
-            if (m.levels[linked + j] > dev_maxlevel) { B = j + 1; break; }  // new top level ends the batch
-        off.resize(B); lp.clear(); ll.clear();
-        for (size_t j = 0; j < B; j++) {
-            off[j] = (uint32_t)lp.size();
-            const int top = std::min(m.levels[linked + j], dev_maxlevel);
-            for (int l = 0; l <= top; l++) { lp.push_back((uint32_t)(linked + j)); ll.push_back((uint32_t)l); }
-        }
-        if (lp.size() > max_lists) {  // cannot happen with P(level >= 1) = 1/M, but never overrun the pool
-            size_t j = B;
-            while (j > 1 && off[j - 1] + 8 > max_lists) j--;
-            B = j;
-            off.resize(B);
-            size_t keep = 0;
-            for (size_t i = 0; i < lp.size(); i++) if (lp[i] < linked + B) keep = i + 1;
-            lp.resize(keep); ll.resize(keep);
-        }
-        B200_CUDA_OK(cudaMemcpyAsync(bld.list_off, off.data(), B * 4, cudaMemcpyHostToDevice, stream));
-        B200_CUDA_OK(cudaMemcpyAsync(bld.list_point, lp.data(), lp.size() * 4, cudaMemcpyHostToDevice, stream));
-        B200_CUDA_OK(cudaMemcpyAsync(bld.list_level, ll.data(), ll.size() * 4, cudaMemcpyHostToDevice, stream));
-        a.first = (uint32_t)linked; a.batch = (uint32_t)B; a.lists = (uint32_t)lp.size();
-        a.entry = dev_entry; a.maxlevel = dev_maxlevel;
-        rc = prm.metric == B200HNSW_L2 ? run_batch_metric<0>(a, smem_search, smem_link, &h_aff, stream)
-                                       : run_batch_metric<1>(a, smem_search, smem_link, &h_aff, stream);
+    if (linked == 0) {
+        dev_entry = 0;
+        dev_maxlevel = m.levels[0];
+        linked = 1;
+    }
+    for (const BatchPlan &bp : plan) {
+        a.first = bp.first; a.batch = bp.batch; a.lists = bp.lists;
+        a.entry = bp.entry; a.maxlevel = bp.maxlevel;
+        a.list_off = d_off + (bp.first - linked0);
+        a.list_point = d_lp + bp.lists_off;
+        a.list_level = d_ll + bp.lists_off;
+        rc = nb ? build_run_batch_insert_nb(prm.metric, a, smem_search, smem_link, stream)
+                : build_run_batch_insert(prm.metric, a, smem_search, smem_link, stream);
+        if (rc) break;
         launches += 3;
-        const size_t last = linked + B - 1;
+        const size_t last = (size_t)bp.first + bp.batch - 1;
         if (m.levels[last] > dev_maxlevel) {
             dev_entry = (uint32_t)last;
             dev_maxlevel = m.levels[last];
         }
-        linked += B;
+        linked = (size_t)bp.first + bp.batch;
     }
     if (rc == 0) {
         B200_CUDA_OK(cudaEventRecord(e1, stream));
         B200_CUDA_OK(cudaStreamSynchronize(stream));
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        unsigned long long w[4] = {0, 0, 0, 0};
-        B200_CUDA_OK(cudaMemcpy(w, bld.work, 32, cudaMemcpyDeviceToHost));
+        unsigned long long w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        B200_CUDA_OK(cudaMemcpy(w, bld.work, 64, cudaMemcpyDeviceToHost));
         stats.queries = n_new;
         stats.dist_evals = w[0]; stats.hops_base = w[1]; stats.hops_upper = w[2]; stats.visited_resets = w[3];
+        stats.dropped_reverse_edges = w[4];
         stats.kernel_launches += launches;
         stats.last_kernel_ms = ms;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (rc) cudaStreamSynchronize(stream);
+    cudaFree(d_off); cudaFree(d_lp); cudaFree(d_ll);
     dev.n = linked;
     mirror_dirty = true;
     flags_dirty = true;
@@ -736,7 +519,8 @@ int HnswIndex::flush() {
 void BuildScratch::release() {
     cudaFree(plevel); cudaFree(cand); cudaFree(cand_cnt); cudaFree(list_off); cudaFree(list_point);
     cudaFree(list_level); cudaFree(incnt); cudaFree(incoming); cudaFree(aff_node); cudaFree(aff_level);
-    cudaFree(aff_count); cudaFree(work); cudaFree(batch_ids);
+    cudaFree(aff_count); cudaFree(work); cudaFree(batch_ids); cudaFree(newlists); cudaFree(stage_rows);
+    cudaFree(stage_labels);
     *this = BuildScratch();
 }
 

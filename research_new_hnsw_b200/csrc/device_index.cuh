@@ -82,4 +82,34 @@ static __global__ void rows_to_bf16_kernel(const float4 *__restrict__ vec, uint3
     vec16[(size_t)r * d16 + c] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
 }
 
+// updatePoint: new vectors / labels of `count` existing elements, staged as [count][d4] float4 rows, scattered to their
+// places (and to the bf16 copy when there is one).  One warp per row.
+static __global__ void scatter_rows_kernel(const float4 *__restrict__ rows, const uint64_t *__restrict__ row_labels,
+                                           const uint32_t *__restrict__ ids, uint32_t count, uint32_t d4, uint32_t d16,
+                                           float4 *__restrict__ vec, uint64_t *__restrict__ labels, uint4 *__restrict__ vec16,
+                                           uint8_t *__restrict__ flags) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x & 31;
+    if (w >= count) return;
+    const uint32_t id = ids[w];
+    for (uint32_t c = lane; c < d4; c += 32) vec[(size_t)id * d4 + c] = rows[(size_t)w * d4 + c];
+    if (lane == 0) {
+        labels[id] = row_labels[w];
+        if (flags) flags[id] = 0;  // an updated element is live (unmarkDeletedInternal precedes updatePoint)
+    }
+    if (vec16) {
+        auto pack = [](float lo, float hi) -> uint32_t {
+            uint32_t l = __float_as_uint(lo), h = __float_as_uint(hi);
+            l = (l + 0x7FFFu + ((l >> 16) & 1u)) >> 16;
+            h = (h + 0x7FFFu + ((h >> 16) & 1u)) >> 16;
+            return l | (h << 16);
+        };
+        for (uint32_t c = lane; c < d16; c += 32) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            if (2 * c < d4) a = rows[(size_t)w * d4 + 2 * c];
+            if (2 * c + 1 < d4) b = rows[(size_t)w * d4 + 2 * c + 1];
+            vec16[(size_t)id * d16 + c] = make_uint4(pack(a.x, a.y), pack(a.z, a.w), pack(b.x, b.y), pack(b.z, b.w));
+        }
+    }
+}
+
 }  // namespace b200

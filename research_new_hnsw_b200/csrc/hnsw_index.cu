@@ -172,14 +172,16 @@ int HnswIndex::upload_all() {
 // delete marks (byte 2 of the level-0 record header, hnswalg.h:934-937) -> device byte array
 // `allowed` (nullable, one byte per internal id) is a BaseFilterFunctor evaluated by the caller: a node that is not
 // allowed is kept out of top_candidates exactly like a deleted one (hnswalg.h:406-407), so both share the flag byte.
-int HnswIndex::upload_flags(const uint8_t *allowed) {
-    if (!flags_dirty && dev.flags && !allowed) return 0;
+int HnswIndex::upload_flags(const uint8_t *allowed, const uint32_t *extra, size_t n_extra) {
+    if (!flags_dirty && dev.flags && !allowed && !n_extra) return 0;
     B200_CUDA_OK(cudaSetDevice(dev.device));
     if (!dev.flags) B200_CUDA_OK(cudaMalloc(&dev.flags, std::max<size_t>(dev.cap, 1)));
     std::vector<uint8_t> f(host.cur);
     for (size_t i = 0; i < host.cur; i++) f[i] = (host.deleted(i) || (allowed && !allowed[i])) ? 1 : 0;
+    for (size_t i = 0; i < n_extra; i++)
+        if (extra[i] < host.cur) f[extra[i]] = 1;
     if (host.cur) B200_CUDA_OK(cudaMemcpy(dev.flags, f.data(), host.cur, cudaMemcpyHostToDevice));
-    flags_dirty = allowed != nullptr;  // a per-call filter must not outlive its call
+    flags_dirty = allowed != nullptr || n_extra != 0;  // a per-call state must not outlive its call
     return 0;
 }
 
@@ -239,8 +241,20 @@ static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
                                           optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
-    hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE><<<a.nq, TEAM, smem, st>>>(a);
-    B200_CUDA_OK(cudaGetLastError());
+    // programmatic stream serialization: this grid may start while the previous kernel of the stream drains (the kernel
+    // orders its own output writes behind the previous grid with griddepcontrol.wait)
+    static const bool pdl = !(getenv("B200HNSW_PDL") && atoi(getenv("B200HNSW_PDL")) == 0);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(a.nq);
+    cfg.blockDim = dim3(TEAM);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE>, a));
     return 0;
 }
 
@@ -320,6 +334,10 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.flags = nonbare ? dev.flags : nullptr;
     a.bufcap = (uint32_t)(nonbare ? 2 * efx : efx);
     a.hash_bits = pick_hash_bits(a.bufcap, list_cap, team);
+    {
+        static const int pf_env = getenv("B200HNSW_PF") ? atoi(getenv("B200HNSW_PF")) : -1;
+        a.pf = pf_env >= 0 ? (uint32_t)pf_env : (kPfRows | kPfGreedy);
+    }
     const SearchSmem L(a.bufcap, (uint32_t)list_cap, a.d4, a.hash_bits);
     if (L.total > 226 * 1024) {
         set_error("search configuration needs more than 226 KB of shared memory");

@@ -21,6 +21,12 @@ struct BuildScratch {
     uint32_t *aff_node = nullptr, *aff_level = nullptr, *aff_count = nullptr;
     unsigned long long *work = nullptr;
     size_t cand_efc = 0;
+    // updatePoint: re-pruned neighbour lists of the first phase, staging of the new rows / labels
+    uint32_t *newlists = nullptr;
+    size_t newlists_cap = 0;
+    float *stage_rows = nullptr;
+    uint64_t *stage_labels = nullptr;
+    size_t stage_cap = 0;
     void release();
 };
 
@@ -67,7 +73,9 @@ struct HnswIndex {
     int upload_all();                       // host mirror -> HBM (after load)
     int upload_upper();                     // rebuild up_base / links_up from the host mirror
     int ensure_scratch(size_t nq, size_t k);
-    int upload_flags(const uint8_t *allowed = nullptr);
+    // extra: internal ids uploaded as deleted although the host image says live (relink_points)
+    int upload_flags(const uint8_t *allowed = nullptr, const uint32_t *extra = nullptr, size_t n_extra = 0);
+    bool revived_on_device = false;
     int sync_bf16(size_t first, size_t count);
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
                       uint32_t *dw, cudaStream_t st, const uint8_t *allowed = nullptr);
@@ -80,7 +88,7 @@ struct HnswIndex {
     // build.cu: scratch + batch-independent kernel arguments (args is a BuildArgs*)
     int prepare_build(void *args, size_t max_batch, size_t *max_lists, size_t *smem_search, size_t *smem_link);
     // build.cu: updatePoint for ids that are already linked (vectors in the host image are the new ones); mu held
-    int relink_points(std::vector<uint32_t> ids);
+    int relink_points(std::vector<uint32_t> ids, const std::vector<uint32_t> &revived = {});
     int sync_host_mirror();
 };
 

@@ -50,6 +50,7 @@ struct SearchArgs {
     uint32_t dim, d4, maxM, maxM0;
     uint32_t nq, k, ef;
     uint32_t hash_bits;
+    uint32_t pf;              // GraphView::pf (L2 prefetch policy)
 };
 
 // shared-memory carve-up, shared by host (size) and device (pointers)
@@ -78,6 +79,39 @@ __device__ __forceinline__ float group_sum(float v, uint32_t gmask) {
     for (int o = LPV / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
     return v;
 }
+
+// L2 prefetch (prefetch.global.L2: fire and forget, per-thread address, no register or shared-memory cost).  The
+// gather of a hop runs in rounds of 2 rows per lane group (the bytes in flight are paid in registers); prefetching the
+// rows of the LATER rounds when the hop starts turns their DRAM latency into an L2 hit.  (cp.async.bulk.prefetch.L2
+// would cover a whole row per instruction, but it takes a warp-uniform address: ptxas serialises divergent lanes in
+// a 7-instruction loop per lane, more than the four per-line prefetches it replaces.)
+#ifndef B200_PF_LINE
+#define B200_PF_LINE 128
+#endif
+constexpr uint32_t kPfLine = B200_PF_LINE;
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// rows ids[first..n) of `bytes` each, one thread per 128-byte line
+template <int TEAM>
+__device__ __forceinline__ void prefetch_rows(const char *base, uint32_t bytes, const uint32_t *ids, int first, int n) {
+    const uint32_t lpr = (bytes + kPfLine - 1) / kPfLine;
+    const uint32_t total = (uint32_t)max(n - first, 0) * lpr;
+    for (uint32_t i = threadIdx.x; i < total; i += TEAM) {
+        const uint32_t r = i / lpr, l = i - r * lpr;
+        prefetch_l2(base + (size_t)ids[first + r] * bytes + l * kPfLine);
+    }
+}
+__device__ __forceinline__ void prefetch_span(const char *p, uint32_t bytes) {
+    for (uint32_t o = 0; o < bytes; o += kPfLine) prefetch_l2(p + o);
+}
+// GraphView::pf bits
+constexpr uint32_t kPfRows = 1;      // beam search: rows of gather rounds >= 2 of the current hop
+constexpr uint32_t kPfGreedy = 2;    // greedy descent: same
+constexpr uint32_t kPfNewBest = 4;   // list of an admitted neighbour that beats the predicted next expansion
+constexpr uint32_t kPfRound1 = 8;    // also the rows of round 1 (A/B only)
+constexpr uint32_t kPfSpec = 16;     // rows of the predicted next expansion's neighbours (speculative)
+constexpr uint32_t kPfSpecFilter = 32;  // ... skipping neighbours already in the visited table
+constexpr uint32_t kPfEarly = 64;    // every new neighbour's row as soon as its id passed the visited filter (before the
+                                     // compaction barrier) / every list entry's row in the greedy descent
 
 // One 128-bit chunk of the distance sum on sm_100a's packed fp32 pipe (FFMA2: two fused multiply-adds per
 // instruction): L2 -> diff = fma(v, -1, q), acc = fma(diff, diff, acc); IP -> acc = fma(q, v, acc).  The two halves
@@ -155,7 +189,9 @@ __device__ __forceinline__ void eval_list(const float4 (&q)[CPL], const float4 *
 template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false>
 __device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 *__restrict__ vec, uint32_t d4,
                                            const uint32_t *ids, int n, bool full, float bound, uint64_t *acc,
-                                           int *s_acc, int grp, int sub, const uint8_t *__restrict__ flags = nullptr) {
+                                           int *s_acc, int grp, int sub, const uint8_t *__restrict__ flags = nullptr,
+                                           const uint32_t *__restrict__ pf_lists = nullptr, uint32_t pf_bytes = 0,
+                                           float pf_below = 0.f) {
     constexpr int NGRP = TEAM / LPV;
     const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
     for (int j = grp; j < n; j += 2 * NGRP) {
@@ -195,6 +231,10 @@ __device__ __forceinline__ void eval_admit(const float4 (&q)[CPL], const float4 
         if (sub == 0) {
             if (!full || sa < bound) acc[atomicAdd(s_acc, 1)] = make_key(sa, ida | dela);
             if (has2 && (!full || sb < bound)) acc[atomicAdd(s_acc, 1)] = make_key(sb, idb | delb);
+            if (pf_lists) {  // a neighbour closer than the predicted next expansion will be expanded before it
+                if (sa < pf_below) prefetch_span((const char *)pf_lists + (size_t)ida * pf_bytes, pf_bytes);
+                if (has2 && sb < pf_below) prefetch_span((const char *)pf_lists + (size_t)idb * pf_bytes, pf_bytes);
+            }
         }
     }
 }
@@ -283,6 +323,7 @@ struct GraphView {
     uint32_t d4, maxM, maxM0;
     const uint4 *vec16 = nullptr;  // optional bf16 copy [n][d16], 8 elements per 128-bit chunk (storage variant)
     uint32_t d16 = 0;
+    uint32_t pf = 0;               // kPf* bits: L2 prefetch policy of the traversal
     __device__ __forceinline__ const uint32_t *list(uint32_t node, int level) const {
         return level == 0 ? links0 + (size_t)node * maxM0
                           : links_up + ((size_t)__ldg(up_base + node) + (uint32_t)(level - 1)) * maxM;
@@ -297,7 +338,7 @@ struct TeamCtx {
     float *dist;
     uint32_t *pref;   // neighbour list prefetched for the predicted next expansion
     uint32_t *hash;
-    int *s_cnt, *s_next, *s_best, *s_acc, *s_pref, *s_size, *s_nr;
+    int *s_cnt, *s_next, *s_best, *s_acc, *s_pref, *s_size, *s_nr, *s_pd;
     uint32_t hash_bits;
     template <class Smem>
     __device__ __forceinline__ void bind(unsigned char *smem, const Smem &L, int *ints, uint32_t bits) {
@@ -309,11 +350,11 @@ struct TeamCtx {
         pref = (uint32_t *)(smem + L.off_pref);
         hash = (uint32_t *)(smem + L.off_hash);
         s_cnt = ints; s_next = ints + 1; s_best = ints + 2; s_acc = ints + 3; s_pref = ints + 4;
-        s_size = ints + 5; s_nr = ints + 6;
+        s_size = ints + 5; s_nr = ints + 6; s_pd = ints + 7;
         hash_bits = bits;
     }
 };
-constexpr int kTeamInts = 7;
+constexpr int kTeamInts = 8;
 
 struct WorkCounters {
     uint32_t D = 0, H0 = 0, Hup = 0, resets = 0;
@@ -338,9 +379,12 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
             if (b0 + tid < g.maxM) {
                 nid = __ldg(lst + b0 + tid);
                 c.ids[b0 + tid] = nid;
+                if ((g.pf & kPfEarly) && nid != kEmpty) prefetch_span((const char *)(g.vec + (size_t)nid * g.d4), g.d4 * 16);
             }
             cnt += __syncthreads_count(nid != kEmpty);
         }
+        if ((g.pf & (kPfGreedy | kPfEarly)) == kPfGreedy)
+            prefetch_rows<TEAM>((const char *)g.vec, g.d4 * 16, c.ids, 2 * (TEAM / LPV), cnt);
         eval_list<TEAM, LPV, CPL, METRIC>(q, g.vec, g.d4, c.ids, cnt, c.dist, grp, sub);
         __syncthreads();
         w.D += cnt;
@@ -447,6 +491,9 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[S
             }
             bool isnew = false;
             if (nid != kEmpty) isnew = hash_insert(c.hash, c.hash_bits, nid);
+            if ((g.pf & kPfEarly) && isnew)
+                prefetch_span(STORE ? (const char *)(g.vec16 + (size_t)nid * g.d16) : (const char *)(g.vec + (size_t)nid * g.d4),
+                              STORE ? g.d16 * 16 : g.d4 * 16);
             const uint32_t m = __ballot_sync(0xffffffffu, isnew);
             int basepos = 0;
             if (lane == 0 && m) basepos = atomicAdd(c.s_cnt, __popc(m));
@@ -460,21 +507,34 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[S
             const int pos = next + 1 + lane;
             const bool un = pos < size && !((uint32_t)src[pos] & kExpanded);
             const uint32_t b = __ballot_sync(0xffffffffu, un);
+            float pd = 3.402823466e+38f;  // no other unexpanded entry: any admitted neighbour is expanded next
             if (b) {
-                pnode = (uint32_t)src[next + __ffs(b)] & IDM;
+                const uint64_t pk = src[next + __ffs(b)];
+                pnode = (uint32_t)pk & IDM;
+                pd = ord2f((uint32_t)(pk >> 32));
                 const uint32_t *pl = g.list(pnode, level);
                 if ((uint32_t)lane < llen) pf0 = __ldg(pl + lane);
                 if ((uint32_t)lane + 32 < llen) pf1 = __ldg(pl + lane + 32);
             }
+            if (lane == 0) *c.s_pd = __float_as_int(pd);
         }
         __syncthreads();  // (B) ids[] complete
         const int nnew = *c.s_cnt;
         w.H0 += 1;
         w.D += nnew;
         hcount += nnew;
+        if ((g.pf & (kPfRows | kPfRound1)) && !(g.pf & kPfEarly)) {
+            // rows of the later gather rounds -> L2 now, so only round 1 pays the DRAM latency
+            constexpr int kInFlight = STORE ? 4 * (TEAM / LPV) : 2 * (TEAM / LPV);
+            const uint32_t rb = STORE ? g.d16 * 16 : g.d4 * 16;
+            const char *base = STORE ? (const char *)g.vec16 : (const char *)g.vec;
+            prefetch_rows<TEAM>(base, rb, c.ids, (g.pf & kPfRound1) ? 0 : kInFlight, nnew);
+        }
         if (STORE == 0) {
+            const bool pfl = can_pref && level == 0 && (g.pf & kPfNewBest);
             eval_admit<TEAM, LPV, CPL, METRIC, NB>(reinterpret_cast<const float4(&)[CPL]>(q), g.vec, g.d4, c.ids, nnew, full,
-                                                   bound, c.acc, c.s_acc, grp, sub, flags);
+                                                   bound, c.acc, c.s_acc, grp, sub, flags, pfl ? g.links0 : nullptr,
+                                                   g.maxM0 * 4, pfl ? __int_as_float(*c.s_pd) : 0.f);
         } else {
             constexpr int C16 = (CPL + 1) / 2;
             eval_admit_bf16<TEAM, LPV, C16, METRIC>(reinterpret_cast<const float4(&)[C16][2]>(q), g.vec16, g.d16, c.ids, nnew,
@@ -484,6 +544,29 @@ __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[S
             if ((uint32_t)lane < llen) c.pref[lane] = pf0;
             if ((uint32_t)lane + 32 < llen) c.pref[lane + 32] = pf1;
             if (lane == 0) *c.s_pref = (int)pnode;
+            if ((g.pf & kPfSpec) && pnode != kEmpty) {
+                // speculative: the rows the predicted expansion will gather (it is the best existing candidate, so
+                // even when a new neighbour overtakes it, it is usually expanded a hop or two later, while the rows
+                // are still in the 126 MB L2)
+                const uint32_t rb = STORE ? g.d16 * 16 : g.d4 * 16;
+                const char *base = STORE ? (const char *)g.vec16 : (const char *)g.vec;
+                const uint32_t hm = (1u << c.hash_bits) - 1u;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t id = h ? pf1 : pf0;
+                    bool want = id != kEmpty;
+                    if (want && (g.pf & kPfSpecFilter)) {  // read-only probe of the visited table
+                        uint32_t hh = (id * 0x9E3779B1u) >> (32 - c.hash_bits);
+                        for (;;) {
+                            const uint32_t v = c.hash[hh];
+                            if (v == id) { want = false; break; }
+                            if (v == kEmpty) break;
+                            hh = (hh + 1) & hm;
+                        }
+                    }
+                    if (want) prefetch_span(base + (size_t)id * rb, rb);
+                }
+            }
         }
         __syncthreads();  // (C) acc[] complete, prefetched list stored
         const int m = *c.s_acc;
@@ -567,12 +650,18 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
     GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
     g.vec16 = p.vec16;
     g.d16 = p.d16;
+    g.pf = p.pf;
 
     const int tid = threadIdx.x;
     const int sub = tid % LPV, grp = tid / LPV;
     const uint32_t qi = blockIdx.x;
     const uint32_t d4 = p.d4;
     const uint32_t HS = 1u << p.hash_bits;
+    // Programmatic dependent launch: batches are independent, so the next batch's grid may start filling SMs as soon
+    // as every CTA of this one has been scheduled -- the tail of batch i (SMs draining their last queries) overlaps the
+    // head of batch i+1.  Outputs are written only after griddepcontrol.wait (= the previous grid has completed and
+    // flushed), so stream order of everything a consumer can observe is unchanged.  No-ops without the launch attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
 
     // ---- stage the query (rows of Q are only 4-byte aligned when dim % 4 != 0) and clear the visited table ----
     for (uint32_t i = tid; i < d4 * 4; i += TEAM) qs[i] = i < p.dim ? p.Q[(size_t)qi * p.dim + i] : 0.f;
@@ -622,6 +711,7 @@ __global__ void __launch_bounds__(TEAM, CPL <= 4 ? 1024 / TEAM : 512 / TEAM) hns
     }
 
     // ---- epilogue: first k entries are the result, closest first (hnswalg.h:1315-1322) ----
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint64_t *res = cb ? c.buf_b : c.buf_a;
     if (STORE == 1) {
         // bf16 traversal: re-evaluate the final buffer with the fp32 rows and re-sort it, so distances are the fp32

@@ -23,7 +23,7 @@ def test_exports_every_declared_symbol(lib):
     assert not missing, missing
     from research_new_hnsw_b200 import capi
     assert sorted(capi.EXPORTS) == names
-    assert L.b200hnsw_abi_version() == 1
+    assert L.b200hnsw_abi_version() == 2
 
 
 def test_no_cpu_fallback(lib):
