@@ -110,8 +110,9 @@ int b200hnsw_set_ef(b200hnsw_index *h, size_t ef);
  * level generator (hnswalg.h:207-211,1187-1198,1255-1265); graph linking may be deferred until b200hnsw_flush
  * (or any call that reads the graph).  labels == NULL means labels cur_element_count .. +n-1.
  * A label that already exists is UPDATED (hnswalg.h:1157-1174 -> updatePoint, :995-1139): new vector, delete mark
- * cleared, and the point is re-linked on the GPU (repairConnectionsForUpdate, :1075-1139; the re-pruning of its old
- * neighbours, :1009-1069, is not performed). */
+ * cleared, every old neighbour re-pruned over the 1-hop + 2-hop set (:1009-1069) and the point re-linked
+ * (repairConnectionsForUpdate, :1075-1139), all on the GPU.  Up to 2048 updates per call are applied one after the other
+ * like the reference does; larger calls in groups that see the graph as of the start of their group. */
 int b200hnsw_add_batch(b200hnsw_index *h, const float *X, const uint64_t *labels, size_t n);
 /* addPoint(data, label, replace_deleted = true), hnswalg.h:954-992: while deleted elements exist, each row takes the
  * place of one of them (its label and vector replaced, delete mark cleared, re-linked like an update); otherwise like
@@ -121,7 +122,9 @@ int b200hnsw_add_batch_replace_deleted(b200hnsw_index *h, const float *X, const 
 int b200hnsw_flush(b200hnsw_index *h);
 /* searchKnn, hnswalg.h:1270-1324, batched: nq queries of dim floats; ef = 0 -> the setEf value; the engine uses
  * max(ef, k) as the reference does (hnswalg.h:1309).  labels_out/dists_out are [nq][k]; counts_out (nullable)
- * receives the number of valid results per query; work_out (nullable) receives [nq][4] = {D, H0, Hup, resets}. */
+ * receives the number of valid results per query; work_out (nullable) receives [nq][4] = {D, H0, Hup, resets}.
+ * Limits (B200HNSW_E_UNSUPPORTED beyond them; the reference has none): max(ef, k) <= 4096, dim <= 1024, and while
+ * elements are marked deleted or a filter is given at most 2^30 elements (one id bit carries the mark). */
 int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef, uint64_t *labels_out,
                           float *dists_out, uint32_t *counts_out, uint32_t *work_out);
 /* Same, with DEVICE pointers on the index's device, enqueued on cuda_stream (a cudaStream_t; NULL = legacy
@@ -169,6 +172,34 @@ int b200hnsw_merge_topk_device(const uint64_t *d_labels_in, const float *d_dists
 int b200hnsw_merge_topk_packed_device(const void *d_blocks, size_t block_bytes, size_t shards, size_t nq, size_t k,
                                       uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream);
 
+/* ---- sharded index: one process, one sub-index per GPU ---------------------------------------
+ * The reference has no sharding; north_star prescribes it: the data set is split into n_shards HierarchicalNSW
+ * sub-indexes, shard s on CUDA device devices[s] (devices may repeat), every query is searched on every shard and the
+ * per-shard top-k are merged by (dist, label) on devices[0].  Inside one process the exchange needs no collective:
+ * with peer access every shard's search kernel stores its rows straight into the root device's packed buffer over
+ * NVLink, otherwise the block is copied device to device.  Each shard is an ordinary index: its file is a reference
+ * saveIndex file that the reference (or b200hnsw_load) opens on its own.  Labels are global; a label lives on shard
+ * label % n_shards, so re-adding a label updates it where it is.  params->max_elements is PER SHARD. */
+typedef struct b200hnsw_sharded b200hnsw_sharded;
+int b200hnsw_sharded_create(const b200hnsw_params *params, const int *devices, size_t n_shards, b200hnsw_sharded **out);
+/* paths[s] = saveIndex file of shard s (hnswalg.h:716-822 per shard). */
+int b200hnsw_sharded_load(const char *const *paths, const b200hnsw_params *params, const int *devices, size_t n_shards,
+                          b200hnsw_sharded **out);
+int b200hnsw_sharded_save(b200hnsw_sharded *h, const char *const *paths);
+void b200hnsw_sharded_destroy(b200hnsw_sharded *h);
+int b200hnsw_sharded_num_shards(b200hnsw_sharded *h, size_t *n_out);
+/* Borrowed handle of one shard (valid until b200hnsw_sharded_destroy): every b200hnsw_* call applies to it. */
+int b200hnsw_sharded_get_shard(b200hnsw_sharded *h, size_t shard, b200hnsw_index **out);
+int b200hnsw_sharded_count(b200hnsw_sharded *h, uint64_t *count_out);
+/* addPoint, routed by label (labels == NULL: consecutive labels continuing the running count). */
+int b200hnsw_sharded_add_batch(b200hnsw_sharded *h, const float *X, const uint64_t *labels, size_t n);
+int b200hnsw_sharded_flush(b200hnsw_sharded *h);
+/* searchKnn over all shards: rows as b200hnsw_search_batch; ef is applied to every shard. */
+int b200hnsw_sharded_search_batch(b200hnsw_sharded *h, const float *Q, size_t nq, size_t k, size_t ef,
+                                  uint64_t *labels_out, float *dists_out, uint32_t *counts_out);
+/* CUDA-event time of the last sharded search (H2D of the queries on every device .. merge kernel), milliseconds. */
+int b200hnsw_sharded_last_ms(b200hnsw_sharded *h, double *ms_out);
+
 /* ---- BruteforceSearch<float> (bruteforce.h) -------------------------------------------------------------- */
 /* BruteforceSearch(space, maxElements), bruteforce.h:48-59 */
 int b200bf_create(const b200hnsw_params *params, b200bf_index **out);
@@ -184,6 +215,13 @@ int b200bf_remove(b200bf_index *h, uint64_t label);
 /* searchKnn, bruteforce.h:106-135, batched: the k lexicographically smallest (dist, label) pairs per query. */
 int b200bf_search_batch(b200bf_index *h, const float *Q, size_t nq, size_t k, uint64_t *labels_out,
                         float *dists_out, uint32_t *counts_out);
+/* searchKnn with a BaseFilterFunctor (bruteforce.h:114,121: rows the functor rejects are skipped).  As for the graph
+ * index the caller evaluates the host callback once per stored ROW and passes the verdicts: allowed[i] != 0 for row i
+ * (rows in storage order, b200bf_get_labels gives their labels), b200bf_count bytes. */
+int b200bf_search_batch_filtered(b200bf_index *h, const float *Q, size_t nq, size_t k, const uint8_t *allowed,
+                                 uint64_t *labels_out, float *dists_out, uint32_t *counts_out);
+/* label of every stored row, in storage order (bruteforce.h:51-52: the label sits behind the vector). */
+int b200bf_get_labels(b200bf_index *h, uint64_t *labels_out, size_t capacity);
 int b200bf_search_batch_device(b200bf_index *h, const float *dQ, size_t nq, size_t k, uint64_t *d_labels_out,
                                float *d_dists_out, uint32_t *d_counts_out, void *cuda_stream);
 int b200bf_count(b200bf_index *h, uint64_t *count_out);

@@ -53,9 +53,12 @@ EXPORTS = [
     "b200hnsw_search_batch", "b200hnsw_search_batch_filtered", "b200hnsw_get_labels", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
     "b200hnsw_get_linklist", "b200hnsw_get_label", "b200hnsw_get_data", "b200hnsw_get_data_by_label",
     "b200hnsw_mark_delete", "b200hnsw_unmark_delete", "b200hnsw_resize", "b200hnsw_index_file_size",
-    "b200hnsw_get_stats", "b200hnsw_merge_topk_device", "b200hnsw_merge_topk_packed_device", "b200bf_create", "b200bf_load", "b200bf_save",
+    "b200hnsw_get_stats", "b200hnsw_sharded_create", "b200hnsw_sharded_load", "b200hnsw_sharded_save",
+    "b200hnsw_sharded_destroy", "b200hnsw_sharded_num_shards", "b200hnsw_sharded_get_shard", "b200hnsw_sharded_count",
+    "b200hnsw_sharded_add_batch", "b200hnsw_sharded_flush", "b200hnsw_sharded_search_batch", "b200hnsw_sharded_last_ms",
+    "b200hnsw_merge_topk_device", "b200hnsw_merge_topk_packed_device", "b200bf_create", "b200bf_load", "b200bf_save",
     "b200bf_destroy", "b200bf_add_batch", "b200bf_remove", "b200bf_search_batch", "b200bf_search_batch_device",
-    "b200bf_count", "b200bf_get_stats",
+    "b200bf_search_batch_filtered", "b200bf_get_labels", "b200bf_count", "b200bf_get_stats",
 ]
 
 
@@ -110,6 +113,18 @@ def load_library():
     L.b200hnsw_resize.argtypes = [vp, sz]
     L.b200hnsw_index_file_size.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.b200hnsw_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+    L.b200hnsw_sharded_create.argtypes = [C.POINTER(_Params), C.POINTER(C.c_int), sz, C.POINTER(vp)]
+    L.b200hnsw_sharded_load.argtypes = [C.POINTER(C.c_char_p), C.POINTER(_Params), C.POINTER(C.c_int), sz, C.POINTER(vp)]
+    L.b200hnsw_sharded_save.argtypes = [vp, C.POINTER(C.c_char_p)]
+    L.b200hnsw_sharded_destroy.argtypes = [vp]
+    L.b200hnsw_sharded_destroy.restype = None
+    L.b200hnsw_sharded_num_shards.argtypes = [vp, C.POINTER(sz)]
+    L.b200hnsw_sharded_get_shard.argtypes = [vp, sz, C.POINTER(vp)]
+    L.b200hnsw_sharded_count.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.b200hnsw_sharded_add_batch.argtypes = [vp, vp, vp, sz]
+    L.b200hnsw_sharded_flush.argtypes = [vp]
+    L.b200hnsw_sharded_search_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
+    L.b200hnsw_sharded_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.b200hnsw_merge_topk_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     L.b200hnsw_merge_topk_packed_device.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
     L.b200bf_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
@@ -121,6 +136,8 @@ def load_library():
     L.b200bf_remove.argtypes = [vp, C.c_uint64]
     L.b200bf_search_batch.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     L.b200bf_search_batch_device.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp]
+    L.b200bf_search_batch_filtered.argtypes = [vp, vp, sz, sz, vp, vp, vp, vp]
+    L.b200bf_get_labels.argtypes = [vp, vp, sz]
     L.b200bf_count.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.b200bf_get_stats.argtypes = [vp, C.POINTER(_Stats)]
     _LIB = L
@@ -183,10 +200,17 @@ class HierarchicalNSW:
             p = _params(space, int(arg), M, ef_construction, random_seed, allow_replace_deleted, storage, device)
             _chk(self._L.b200hnsw_create(C.byref(p), C.byref(self._h)))
 
+    @classmethod
+    def _borrowed(cls, space, handle, owner):
+        """view of a shard owned by a ShardedHierarchicalNSW (never destroyed from here)"""
+        self = cls.__new__(cls)
+        self._L, self.space, self._h, self._owner = load_library(), space, handle, owner
+        return self
+
     def __del__(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and not getattr(self, "_owner", None):
             self._L.b200hnsw_destroy(self._h)
-            self._h = None
+        self._h = None
 
     # ---- public fields of the reference class -------------------------------------------------
     def info(self):
@@ -333,6 +357,72 @@ class HierarchicalNSW:
         return {n: getattr(s, n) for n, _ in _Stats._fields_}
 
 
+class ShardedHierarchicalNSW:
+    """One process, one HierarchicalNSW sub-index per device (include/b200hnsw.h, b200hnsw_sharded_*):
+    every query is searched on every shard, per-shard top-k are merged on devices[0].  ``arg`` is the per-shard capacity
+    (build) or a list of per-shard saveIndex files (load)."""
+
+    def __init__(self, space, arg, devices, M=16, ef_construction=200, random_seed=100, storage=F32):
+        self._L = load_library()
+        self.space = space
+        self._h = C.c_void_p()
+        dv = (C.c_int * len(devices))(*devices)
+        if isinstance(arg, (list, tuple)):
+            assert len(arg) == len(devices)
+            p = _params(space, 0, 0, 0, 0, False, storage)
+            paths = (C.c_char_p * len(arg))(*[os.fsencode(a) for a in arg])
+            _chk(self._L.b200hnsw_sharded_load(paths, C.byref(p), dv, len(devices), C.byref(self._h)))
+        else:
+            p = _params(space, int(arg), M, ef_construction, random_seed, False, storage)
+            _chk(self._L.b200hnsw_sharded_create(C.byref(p), dv, len(devices), C.byref(self._h)))
+        self.n_shards = len(devices)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200hnsw_sharded_destroy(self._h)
+            self._h = None
+
+    def shard(self, s):
+        h = C.c_void_p()
+        _chk(self._L.b200hnsw_sharded_get_shard(self._h, s, C.byref(h)))
+        return HierarchicalNSW._borrowed(self.space, h, self)
+
+    @property
+    def cur_element_count(self):
+        v = C.c_uint64()
+        _chk(self._L.b200hnsw_sharded_count(self._h, C.byref(v)))
+        return v.value
+
+    def addPoints(self, X, labels=None):
+        X = np.ascontiguousarray(X, np.float32)
+        assert X.ndim == 2 and X.shape[1] == self.space.dim
+        if labels is not None:
+            labels = np.ascontiguousarray(labels, np.uint64)
+        _chk(self._L.b200hnsw_sharded_add_batch(self._h, _ptr(X), _ptr(labels), X.shape[0]))
+
+    def flush(self):
+        _chk(self._L.b200hnsw_sharded_flush(self._h))
+
+    def saveIndex(self, locations):
+        paths = (C.c_char_p * len(locations))(*[os.fsencode(a) for a in locations])
+        _chk(self._L.b200hnsw_sharded_save(self._h, paths))
+
+    def searchKnnBatch(self, Q, k, ef=0):
+        Q = np.ascontiguousarray(Q, np.float32)
+        assert Q.ndim == 2 and Q.shape[1] == self.space.dim
+        nq = Q.shape[0]
+        labels = np.empty((nq, k), np.uint64)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        _chk(self._L.b200hnsw_sharded_search_batch(self._h, _ptr(Q), nq, k, ef, _ptr(labels), _ptr(dists), _ptr(counts)))
+        return dict(labels=labels, dists=dists, counts=counts)
+
+    def last_ms(self):
+        v = C.c_double()
+        _chk(self._L.b200hnsw_sharded_last_ms(self._h, C.byref(v)))
+        return v.value
+
+
 class BruteforceSearch:
     """hnswlib::BruteforceSearch<float> (bruteforce.h:10)."""
 
@@ -388,6 +478,21 @@ class BruteforceSearch:
         r = self.searchKnnBatch(np.asarray(query, np.float32).reshape(1, -1), k)
         n = int(r["counts"][0])
         return [(float(r["dists"][0, j]), int(r["labels"][0, j])) for j in range(n - 1, -1, -1)]
+
+    def searchKnnFiltered(self, Q, k, is_id_allowed):
+        """searchKnn(query, k, isIdAllowed) batched (bruteforce.h:106-135): `is_id_allowed(label) -> bool` plays
+        BaseFilterFunctor; it is evaluated once per stored row on the host, the kernels take the verdicts as a row mask."""
+        Q = np.ascontiguousarray(Q, np.float32)
+        nq, n = Q.shape[0], self.cur_element_count
+        lab = np.empty(max(n, 1), np.uint64)
+        _chk(self._L.b200bf_get_labels(self._h, _ptr(lab), lab.size))
+        allowed = np.fromiter((1 if is_id_allowed(int(l)) else 0 for l in lab[:n]), np.uint8, n)
+        labels = np.empty((nq, k), np.uint64)
+        dists = np.empty((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        _chk(self._L.b200bf_search_batch_filtered(self._h, _ptr(Q), nq, k, _ptr(allowed), _ptr(labels), _ptr(dists),
+                                                  _ptr(counts)))
+        return dict(labels=labels, dists=dists, counts=counts)
 
     def searchKnnDevice(self, dQ, nq, k, d_labels, d_dists, d_counts=0, stream=0):
         _chk(self._L.b200bf_search_batch_device(self._h, dQ, nq, k, d_labels, d_dists, d_counts or None,

@@ -64,7 +64,8 @@ template <int METRIC, int QS, int P>
 __global__ void __launch_bounds__(64 * QS + 32, 1)
     bf_stream_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels, uint32_t n, uint32_t d4,
                      uint32_t lane_chunks, uint32_t dim, const float *__restrict__ Q, uint32_t nq, uint32_t k,
-                     uint32_t stages, float *__restrict__ part_d, uint64_t *__restrict__ part_l) {
+                     uint32_t stages, float *__restrict__ part_d, uint64_t *__restrict__ part_l,
+                     const uint8_t *__restrict__ mask) {
     constexpr int NQT = QS * P, NCOMP = 64 * QS, NCW = NCOMP / 32;
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[kStMaxStages], empty[kStMaxStages];
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(64 * QS + 32, 1)
             float d = __fadd_rn(__fadd_rn(__fadd_rn(acc[p][0], acc[p][1]), acc[p][2]), acc[p][3]);
             d = __fadd_rn(d, tail[p]);
             if (METRIC == 1) d = __fsub_rn(1.0f, d);
-            if (g < n && q0 + qq < nq && d <= __int_as_float(meta[qq * 4 + 3])) {
+            if (g < n && q0 + qq < nq && d <= __int_as_float(meta[qq * 4 + 3]) && (!mask || mask[g])) {
                 const int pos = atomicAdd(&meta[qq * 4 + 2], 1);
                 qd[qq * kStRows + pos] = d;
                 ql[qq * kStRows + pos] = __ldg(labels + g);
@@ -253,12 +254,12 @@ __global__ void bf_stream_counts_kernel(uint32_t *counts, uint32_t nq, uint32_t 
 template <int METRIC, int QS, int P>
 static cudaError_t stream_launch(dim3 grid, uint32_t smem_bytes, cudaStream_t st, const float4 *X, const uint64_t *labels,
                                  uint32_t n, uint32_t d4, uint32_t lane_chunks, uint32_t dim, const float *Q, uint32_t nq,
-                                 uint32_t k, uint32_t stages, float *pd, uint64_t *pl) {
+                                 uint32_t k, uint32_t stages, float *pd, uint64_t *pl, const uint8_t *mask) {
     cudaError_t e = cudaFuncSetAttribute(bf_stream_kernel<METRIC, QS, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem_bytes);
     if (e != cudaSuccess) return e;
     bf_stream_kernel<METRIC, QS, P><<<grid, 64 * QS + 32, smem_bytes, st>>>(X, labels, n, d4, lane_chunks, dim, Q, nq, k,
-                                                                            stages, pd, pl);
+                                                                            stages, pd, pl, mask);
     return cudaGetLastError();
 }
 
@@ -314,10 +315,10 @@ int BruteIndex::search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *d
 #define B200_STREAM_CASE(QS_, P_)                                                                                       \
     e = m == 0 ? stream_launch<0, QS_, P_>(grid, smem_bytes, st, dX, dLabels, (uint32_t)n, (uint32_t)d4,                \
                                            (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_, (uint32_t)nq, (uint32_t)k,  \
-                                           stages, dPartD, dPartL)                                                              \
+                                           stages, dPartD, dPartL, cur_mask)                                            \
                : stream_launch<1, QS_, P_>(grid, smem_bytes, st, dX, dLabels, (uint32_t)n, (uint32_t)d4,                \
                                            (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_, (uint32_t)nq, (uint32_t)k,  \
-                                           stages, dPartD, dPartL)
+                                           stages, dPartD, dPartL, cur_mask)
     switch (pick) {
         case 0: B200_STREAM_CASE(4, 4); break;
         case 1: B200_STREAM_CASE(4, 2); break;
@@ -329,7 +330,9 @@ int BruteIndex::search_stream(const float *dQ_, size_t nq, size_t k, uint64_t *d
     B200_CUDA_OK(e);
     unsigned merges = 0;
     B200_CUDA_OK(merge_tree(dPartL, dPartD, slices, nq, k, dPart2L, dPart2D, dl, dd, st, &merges));
-    if (dc) bf_stream_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(dc, (uint32_t)nq, (uint32_t)std::min(k, n));
+    if (dc)
+        bf_stream_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(
+            dc, (uint32_t)nq, (uint32_t)std::min(k, cur_mask ? cur_mask_rows : n));
     stats.kernel_launches += 1 + merges;
     return 0;
 }

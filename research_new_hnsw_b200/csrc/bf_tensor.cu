@@ -9,13 +9,18 @@
 //   S = X_bf16 . Q_bf16^T            tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 128 rows x 256 queries per
 //                                    accumulator, K streamed in 64-element (128 B, SWIZZLE_128B) chunks by TMA
 //   key(q,x)  = -S (inner product)   or   |x|^2 + |q|^2 - 2 S (L2)          approximate, to MINIMISE
-//   E(q,x)    = c |q| |x| (+ delta (|x|^2+|q|^2) for L2),  c = 2^-8 + 2^-12  >= |key - true key|
-//               (bf16 rounding is 2^-9 relative per operand; fp32 accumulation slack in the 2^-12)
+//   E(q,x)    = c |q| |x| (+ delta (|x|^2+|q|^2) for L2),  c = 2^-7 + 2^-12  >= |key - true key|
+//               (bf16 keeps 8 significant bits: rounding to nearest is 2^-8 relative per operand, so a product is off
+//               by at most (2^-7 + 2^-16)|q_i x_i| and the sum by that times |q||x| (Cauchy-Schwarz); the 2^-12 covers
+//               the fp32 accumulation of up to 1024 terms)
 //   pass 1    every `stride`-th 128-row panel: panelmin[panel][q] = min_x key + E.  Each panel holds a row whose TRUE
 //             key is <= its panelmin, so U(q) = k-th smallest panelmin is an upper bound of the true k-th best key.
-//   pass 2    all panels: emit row x for query q iff key - E <= U(q)  (a superset of the true top-k; ballot-compacted,
-//             one atomicAdd per warp and query column).
-//   re-rank   exact distances of the candidates, k smallest (dist, label), closest first.
+//   pass 2    all panels: emit (row x, key - E) for query q iff key - E <= U(q)  (a superset of the true top-k;
+//             ballot-compacted, one atomicAdd per warp and query column).
+//   re-rank   U2(q) = k-th smallest key + E over the candidates (every candidate's true key is below its key + E, so
+//             U2 bounds the true k-th best key as well, and far more tightly than U: it sees all rows, not a sample);
+//             survivors = candidates with key - E <= U2 (k plus the rows inside the error band, ~1.4 k); only those
+//             get exact distances, then the k smallest (dist, label), closest first.
 //
 // Roles in the 192-thread CTA (Blackwell playbook): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
 // MMA issuer, warps 2-5 = epilogue (tcgen05.ld of their 32-lane quarter).  Pipelines: 4-stage smem ring (full/empty
@@ -29,7 +34,6 @@
 
 #include "bruteforce.cuh"
 #include "mbarrier.cuh"
-#include "search_kernel.cuh"  // eval_list: the coalesced fp32 gather
 
 namespace b200 {
 
@@ -42,7 +46,7 @@ constexpr uint32_t kStageA = kGM * kGK * 2;   // 16 KB
 constexpr uint32_t kStageB = kGN * kGK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageA + kStageB;
 constexpr uint32_t kGemmSmem = kGStages * kStageBytes + 1024 /*align*/ + 8192 /*barriers + per-tile tables*/;
-constexpr float kErrC = 0.00390625f + 0.000244140625f;   // 2^-8 + 2^-12
+constexpr float kErrC = 0.0078125f + 0.000244140625f;   // 2^-7 + 2^-12
 constexpr float kErrDelta = 4e-6f;
 
 struct GemmArgs {
@@ -50,9 +54,10 @@ struct GemmArgs {
     const float *tabB;      // [nq_pad] per-query error slope  (bf_tables_kernel)
     const float *tabT;      // [nq_pad] per-query additive term / threshold
     uint32_t *panelmin;     // [sampled panels][nq_pad] ordered floats (pass 1)
-    uint32_t *cand;         // [nq][cap] row ids (pass 2)
+    uint2 *cand;            // [nq][cap] (row id, bits of key - E without the per-query constant) (pass 2)
     uint32_t *cand_cnt;     // [nq]
     uint32_t n, nq, nq_pad, kchunks, panels, stride, qtiles, cap;
+    const uint8_t *mask;    // [n] row filter of the call (bruteforce.h:114,121) or null
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             }
             const float *B = s_B + tb * kGN, *T = s_T + tb * kGN;
             const uint32_t r = p * kGM + quarter * 32 + lane;
-            const bool rvalid = r < a.n;
+            const bool rvalid = r < a.n && (!a.mask || a.mask[r]);
             const float xn2 = rvalid ? a.xn2[r] : 0.f;
             const float xnorm = sqrtf(xn2);
             const float Ar = METRIC == 1 ? 0.f : (MODE == 0 ? (1.f + kErrDelta) : (1.f - kErrDelta)) * xn2;
@@ -270,7 +275,13 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
                         base = __shfl_sync(0xffffffffu, base, 0);
                         if (hit) {
                             const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                            if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = r;
+                            if (pos < a.cap) {
+                                uint32_t vj = 0;  // v[] lives in registers: select, do not index
+#pragma unroll
+                                for (int jj = 0; jj < 32; jj++) vj = jj == j ? v[jj] : vj;
+                                const float wj = fmaf(B[c * 32 + j], bx, alpha * __uint_as_float(vj));
+                                a.cand[(size_t)q * a.cap + pos] = make_uint2(r, __float_as_uint(wj + Ar));
+                            }
                         }
                     }
                 }
@@ -341,7 +352,8 @@ __global__ void bf_tables_kernel(const float *__restrict__ qn2, const float *__r
 }
 
 // U(q) = k-th smallest of the sampled panel minima (bitwise binary search over the ordered-float domain).
-// Block = 32 queries x 8 slices of the panel range; loads are coalesced over queries.
+// Block = 32 queries x 8 slices of the panel range; loads are coalesced over queries.  Reads the minima 32 times from
+// L2: only used when the staged version below does not fit in shared memory.
 __global__ void __launch_bounds__(256) bf_kth_kernel(const uint32_t *__restrict__ panelmin, uint32_t sampled,
                                                      uint32_t nq_pad, uint32_t nq, uint32_t k, float *__restrict__ thr) {
     __shared__ uint32_t part[8][32];
@@ -363,12 +375,38 @@ __global__ void __launch_bounds__(256) bf_kth_kernel(const uint32_t *__restrict_
     if (y == 0) thr[q] = q >= nq ? -3.402823466e+38f : (sampled < k ? 3.402823466e+38f : ord2f(prefix));
 }
 
+// Same result with the minima of kKthQ queries staged ONCE in shared memory ([sampled][kKthQ] words, one 32-byte sector
+// per panel row), the 32 counting rounds then run out of shared memory: 1.1 ms -> tens of microseconds at C4.
+constexpr int kKthQ = 8;
+__global__ void __launch_bounds__(256) bf_kth_smem_kernel(const uint32_t *__restrict__ panelmin, uint32_t sampled,
+                                                          uint32_t nq_pad, uint32_t nq, uint32_t k, float *__restrict__ thr) {
+    extern __shared__ uint32_t s_pm[];  // [sampled][kKthQ]
+    __shared__ uint32_t s_tot[2][kKthQ];
+    const uint32_t qi = threadIdx.x % kKthQ, slice = threadIdx.x / kKthQ;  // 32 slices of the panel range
+    const uint32_t q0 = blockIdx.x * kKthQ;
+    for (uint32_t i = threadIdx.x; i < sampled * kKthQ; i += 256) s_pm[i] = panelmin[(size_t)(i / kKthQ) * nq_pad + q0 + i % kKthQ];
+    if (threadIdx.x < 2 * kKthQ) s_tot[threadIdx.x / kKthQ][threadIdx.x % kKthQ] = 0;
+    __syncthreads();
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; bit--) {
+        const uint32_t cand = prefix | ((1u << bit) - 1u);
+        uint32_t cnt = 0;
+        for (uint32_t g = slice; g < sampled; g += 256 / kKthQ) cnt += s_pm[g * kKthQ + qi] <= cand ? 1u : 0u;
+        const int par = bit & 1;
+        if (cnt) atomicAdd(&s_tot[par][qi], cnt);
+        __syncthreads();
+        if (s_tot[par][qi] < k) prefix |= 1u << bit;
+        if (threadIdx.x < kKthQ) s_tot[par ^ 1][threadIdx.x] = 0;  // the other parity is read again two rounds later
+        __syncthreads();
+    }
+    const uint32_t q = q0 + qi;
+    if (slice == 0) thr[q] = q >= nq ? -3.402823466e+38f : (sampled < k ? 3.402823466e+38f : ord2f(prefix));
+}
+
 // Re-rank, one CTA per query, in three steps:
-//  A. fast fp32 distances of all candidates: one warp per candidate, coalesced 128-bit loads, FFMA2, shuffle reduce
-//     (the gather of the graph-search kernel, eval_list<.., LPV=32, ..>);
-//  B. bound: U2 = k-th smallest of (fast + E2) with E2 >= |fast - reference-order value|
-//     (E2 = e2 * |q||x| for inner product, e2 * fast for L2 whose terms are all non-negative); survivors are the
-//     candidates with fast - E2 <= U2 -- the true top-k plus near-ties, typically k + a handful;
+//  A. candidates (row, key - E) from pass 2; E is recomputed from the two norms, so key + E = (key - E) + 2E;
+//  B. bound: U2 = k-th smallest key + E over the candidates (bitwise binary search over ordered floats); survivors are
+//     the candidates with key - E <= U2 -- the true top-k plus the rows inside the error band;
 //  C. exact distances of the survivors in the reference's SSE order (same arithmetic as bf_scan_kernel: four lane
 //     accumulators over the first lane_chunks 128-bit chunks, sequential tail, separate multiply and add), rows staged
 //     through shared memory 32 floats at a time so global reads stay coalesced while every thread sums ITS
@@ -377,20 +415,20 @@ constexpr int kRrThreads = 256;
 constexpr int kRrRows = 128;   // survivor rows staged per round of step C
 constexpr int kRrStride = 33;  // floats per staged row (+1: conflict-free column walks)
 
-template <int METRIC, int CPL>
+template <int METRIC>
 __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
                                                               const float *__restrict__ xn2, const float *__restrict__ qn2,
                                                               const float *__restrict__ Q, uint32_t dim, uint32_t d4,
-                                                              uint32_t lane_chunks, const uint32_t *__restrict__ cand,
+                                                              uint32_t lane_chunks, const uint2 *__restrict__ cand,
                                                               const uint32_t *__restrict__ cand_cnt, uint32_t cap, uint32_t k,
-                                                              uint32_t n, float e2, uint64_t *__restrict__ out_l,
+                                                              uint32_t n, uint64_t *__restrict__ out_l,
                                                               float *__restrict__ out_d, uint32_t *__restrict__ out_c,
                                                               uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char sm[];
     float *qs = (float *)sm;                              // [d4*4]
-    float *fd = qs + d4 * 4;                              // [cap] fast distances, later exact distances of survivors
+    float *fd = qs + d4 * 4;                              // [cap] exact distances of the survivors
     uint32_t *ids = (uint32_t *)(fd + cap);               // [cap] candidate rows, later survivor rows
-    uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [cap] survivor labels
+    uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [cap] (key + E, key - E) per candidate, later survivor labels
     float *tile = (float *)(cl + cap);                    // [max(kRrRows*kRrStride, cap)]
     __shared__ uint32_t s_part[kRrThreads / 32];
     __shared__ uint32_t s_cnt;
@@ -402,29 +440,27 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t i = tid; i < d4 * 4; i += kRrThreads) qs[i] = i < dim ? Q[(size_t)q * dim + i] : 0.f;
-    for (uint32_t i = tid; i < cnt; i += kRrThreads) ids[i] = cand[(size_t)q * cap + i];
+    // ---- A: candidates and their error bounds ----
+    const float q2 = qn2[q], qn = sqrtf(q2);
+    float2 *he = (float2 *)cl;  // (key + E, key - E); cl[] proper is only written in step C
+    for (uint32_t i = tid; i < cnt; i += kRrThreads) {
+        const uint2 c = cand[(size_t)q * cap + i];
+        ids[i] = c.x;
+        const float x2 = xn2[c.x];
+        float lo = __uint_as_float(c.y), e;
+        if (METRIC == 1) {
+            e = kErrC * qn * sqrtf(x2);
+        } else {
+            lo += (1.f - kErrDelta) * q2;
+            e = 2.f * kErrC * qn * sqrtf(x2) + kErrDelta * (x2 + q2);
+        }
+        // lo was rounded a few times on its way here: widen both sides by a relative 2^-20 of the magnitudes involved
+        const float slack = 9.5367431640625e-07f * (fabsf(lo) + e + (METRIC == 0 ? x2 + q2 : 0.f));
+        he[i] = make_float2(lo + 2.f * e + slack, lo - slack);
+    }
     if (tid == 0) s_cnt = 0;
     __syncthreads();
-    // ---- A: fast distances ----
-    {
-        float4 qr[CPL];
-#pragma unroll
-        for (int c = 0; c < CPL; c++) {
-            const uint32_t idx = lane + c * 32;
-            qr[c] = idx < d4 ? ((const float4 *)qs)[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        eval_list<kRrThreads, 32, CPL, METRIC>(qr, X, d4, ids, (int)cnt, fd, warp, lane);
-    }
-    __syncthreads();
-    // ---- B: U2 = k-th smallest of fast + E2 (bitwise binary search over ordered floats) ----
-    const float qn = sqrtf(qn2[q]);
-    float2 *he = (float2 *)cl;  // (fast + E2, fast - E2); cl[] proper is only written in step C
-    for (uint32_t i = tid; i < cnt; i += kRrThreads) {
-        const float f = fd[i];
-        const float e = METRIC == 1 ? e2 * qn * sqrtf(xn2[ids[i]]) : e2 * fabsf(f);
-        he[i] = make_float2(f + e, f - e);
-    }
-    __syncthreads();
+    // ---- B: U2 = k-th smallest of key + E (bitwise binary search over ordered floats) ----
     uint32_t prefix = 0;
     if (cnt > k) {
         for (int bit = 31; bit >= 0; bit--) {
@@ -460,6 +496,11 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     const uint32_t ns = s_cnt;  // <= cnt <= cap words fit in tile[] (sized max(kRrRows*kRrStride, cap))
     for (uint32_t i = tid; i < ns; i += kRrThreads) ids[i] = surv[i];
     __syncthreads();
+    // the rows of the first round are on their way to L2 while the first stage is set up
+    for (uint32_t i = tid; i < min(ns, (uint32_t)kRrRows) * ((d4 * 16 + 127) / 128); i += kRrThreads) {
+        const uint32_t lpr = (d4 * 16 + 127) / 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(X + (size_t)ids[i / lpr] * d4) + (i % lpr) * 128));
+    }
     // ---- C: exact distances of the survivors in reference order ----
     for (uint32_t base = 0; base < ns; base += kRrRows) {
         const uint32_t nb = min((uint32_t)kRrRows, ns - base);
@@ -531,30 +572,21 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
             out_d[(size_t)q * k + rank] = di;
         }
     }
-    if (tid == 0 && out_c) out_c[q] = min(min(k, n), ns);
+    if (tid == 0 && out_c) out_c[q] = min(min(k, n), ns);  // n = rows that pass the call's filter
 }
 
 template <int METRIC>
-static void launch_rerank(uint32_t d4, unsigned grid, size_t smem, cudaStream_t st, const float4 *X, const uint64_t *labels,
-                          const float *xn2, const float *qn2, const float *Q, uint32_t dim, uint32_t lane_chunks,
-                          const uint32_t *cand, const uint32_t *cand_cnt, uint32_t cap, uint32_t k, uint32_t n, float e2,
+static void launch_rerank(unsigned grid, size_t smem, cudaStream_t st, const float4 *X, const uint64_t *labels,
+                          const float *xn2, const float *qn2, const float *Q, uint32_t dim, uint32_t d4, uint32_t lane_chunks,
+                          const uint2 *cand, const uint32_t *cand_cnt, uint32_t cap, uint32_t k, uint32_t n,
                           uint64_t *out_l, float *out_d, uint32_t *out_c, uint32_t *overflow) {
-#define B200_RR(CPL)                                                                                                     \
-    do {                                                                                                                 \
-        static bool cfg = false;                                                                                         \
-        if (!cfg) {                                                                                                      \
-            cudaFuncSetAttribute(bf_rerank_kernel<METRIC, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-            cfg = true;                                                                                                  \
-        }                                                                                                                \
-        bf_rerank_kernel<METRIC, CPL><<<grid, kRrThreads, smem, st>>>(X, labels, xn2, qn2, Q, dim, d4, lane_chunks, cand, \
-                                                                      cand_cnt, cap, k, n, e2, out_l, out_d, out_c, overflow); \
-    } while (0)
-    if (d4 <= 32) B200_RR(1);
-    else if (d4 <= 64) B200_RR(2);
-    else if (d4 <= 128) B200_RR(4);
-    else if (d4 <= 192) B200_RR(6);
-    else B200_RR(8);
-#undef B200_RR
+    static bool cfg = false;
+    if (!cfg) {
+        cudaFuncSetAttribute(bf_rerank_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cfg = true;
+    }
+    bf_rerank_kernel<METRIC><<<grid, kRrThreads, smem, st>>>(X, labels, xn2, qn2, Q, dim, d4, lane_chunks, cand, cand_cnt, cap,
+                                                            k, n, out_l, out_d, out_c, overflow);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -637,7 +669,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const size_t nq_pad = (nq + kGN - 1) / kGN * kGN;
     const size_t sampled = (panels + stride - 1) / stride;
     // candidate slots per query: k/f + the error band is the expectation; an overflowing batch is retried with 4x
-    size_t cap_c = std::max<size_t>(1024, 8 * k);
+    size_t cap_c = std::max<size_t>(1536, 12 * k);
     if (const char *e = getenv("B200HNSW_BF_CAP")) cap_c = std::max(256, atoi(e));
     cap_c = std::max(cap_c, tz.cap_floor);
     if (nq_pad > tz.q_cap || cap_c != tz.cap) {
@@ -650,7 +682,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
         tz.tabB = tz.tabT = nullptr;
         B200_CUDA_OK(cudaMalloc(&tz.tabB, nq_pad * 4));
         B200_CUDA_OK(cudaMalloc(&tz.tabT, nq_pad * 4));
-        B200_CUDA_OK(cudaMalloc(&tz.cand, nq_pad * cap_c * 4));
+        B200_CUDA_OK(cudaMalloc(&tz.cand, nq_pad * cap_c * 8));
         B200_CUDA_OK(cudaMalloc(&tz.cand_cnt, nq_pad * 4));
         if (!tz.overflow) B200_CUDA_OK(cudaMalloc(&tz.overflow, 4));
         tz.q_cap = nq_pad;
@@ -662,6 +694,14 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
         B200_CUDA_OK(cudaMalloc(&tz.panelmin, sampled * nq_pad * 4));
         tz.pm_elems = sampled * nq_pad;
     }
+    // B200HNSW_BF_PROFILE=1: CUDA events between the stages, printed per call (diagnostic only)
+    static const bool prof = getenv("B200HNSW_BF_PROFILE") && atoi(getenv("B200HNSW_BF_PROFILE")) != 0;
+    cudaEvent_t pe[6] = {};
+    int pn = 0;
+    auto mark = [&]() {
+        if (prof && pn < 6) { cudaEventCreate(&pe[pn]); cudaEventRecord(pe[pn], st); pn++; }
+    };
+    mark();
     bf_to_bf16_kernel<<<(unsigned)((nq_pad * 32 + 255) / 256), 256, 0, st>>>(dQ_, host.dim, (uint32_t)host.dim, (uint32_t)kp,
                                                                            (uint32_t)nq, (uint32_t)nq_pad,
                                                                            (__nv_bfloat16 *)tz.qb, tz.qn2);
@@ -672,9 +712,11 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     if (!rc) rc = make_map(&mB, tz.qb, nq_pad, kp, kGN);
     if (rc) return rc;
     GemmArgs a{};
-    a.xn2 = tz.xn2; a.tabB = tz.tabB; a.tabT = tz.tabT; a.panelmin = tz.panelmin; a.cand = tz.cand; a.cand_cnt = tz.cand_cnt;
+    a.xn2 = tz.xn2; a.tabB = tz.tabB; a.tabT = tz.tabT; a.panelmin = tz.panelmin; a.cand = (uint2 *)tz.cand;
+    a.cand_cnt = tz.cand_cnt;
     a.n = (uint32_t)n; a.nq = (uint32_t)nq; a.nq_pad = (uint32_t)nq_pad; a.kchunks = (uint32_t)(kp / kGK);
     a.panels = (uint32_t)panels; a.qtiles = (uint32_t)(nq_pad / kGN); a.cap = (uint32_t)cap_c;
+    a.mask = cur_mask;
     static bool configured[16] = {};
     if (device < 16 && !configured[device]) {
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
@@ -693,14 +735,28 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     unsigned grid = (unsigned)std::min<size_t>((size_t)sms, sampled * a.qtiles);
     if (ip) bf_gemm_kernel<1, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
     else bf_gemm_kernel<0, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
-    bf_kth_kernel<<<(unsigned)(nq_pad / 32), 256, 0, st>>>(tz.panelmin, (uint32_t)sampled, (uint32_t)nq_pad,
-                                                          (uint32_t)nq, (uint32_t)k, tz.thr);
+    mark();
+    const size_t kth_smem = sampled * kKthQ * 4;
+    if (kth_smem <= 160 * 1024) {
+        static bool kcfg = false;
+        if (!kcfg) {
+            B200_CUDA_OK(cudaFuncSetAttribute(bf_kth_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            kcfg = true;
+        }
+        bf_kth_smem_kernel<<<(unsigned)(nq_pad / kKthQ), 256, kth_smem, st>>>(tz.panelmin, (uint32_t)sampled, (uint32_t)nq_pad,
+                                                                             (uint32_t)nq, (uint32_t)k, tz.thr);
+    } else {
+        bf_kth_kernel<<<(unsigned)(nq_pad / 32), 256, 0, st>>>(tz.panelmin, (uint32_t)sampled, (uint32_t)nq_pad,
+                                                              (uint32_t)nq, (uint32_t)k, tz.thr);
+    }
+    mark();
     // pass 2: candidates from all panels
     bf_tables_kernel<<<tgrid, 256, 0, st>>>(tz.qn2, tz.thr, (uint32_t)nq_pad, ip ? 1 : 0, 1, tz.tabB, tz.tabT);
     a.stride = 1;
     grid = (unsigned)std::min<size_t>((size_t)sms, panels * a.qtiles);
     if (ip) bf_gemm_kernel<1, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
     else bf_gemm_kernel<0, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
+    mark();
     // exact re-rank
     const size_t dim = host.dim;
     size_t lane_floats;
@@ -710,20 +766,30 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     else lane_floats = 0;
     const size_t rsm = d4 * 16 + cap_c * 4 + (cap_c + (cap_c & 1)) * 4 + cap_c * 8 +
                        std::max<size_t>((size_t)kRrRows * kRrStride, cap_c) * 4;
-    // |fast fp32 value - reference-order value| <= (longest add chain of either) * 2^-24 * sum|terms|, with slack
-    const float e2 = (float)((double)(dim / 4 + 64) * 1.2e-7);
     if (ip)
-        launch_rerank<1>((uint32_t)d4, (unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim,
-                         (uint32_t)(lane_floats / 4), tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k, (uint32_t)n, e2,
-                         dl, dd, dc, tz.overflow);
+        launch_rerank<1>((unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim, (uint32_t)d4,
+                         (uint32_t)(lane_floats / 4), (const uint2 *)tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k,
+                         (uint32_t)(cur_mask ? cur_mask_rows : n), dl, dd, dc, tz.overflow);
     else
-        launch_rerank<0>((uint32_t)d4, (unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim,
-                         (uint32_t)(lane_floats / 4), tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k, (uint32_t)n, e2,
-                         dl, dd, dc, tz.overflow);
+        launch_rerank<0>((unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim, (uint32_t)d4,
+                         (uint32_t)(lane_floats / 4), (const uint2 *)tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k,
+                         (uint32_t)(cur_mask ? cur_mask_rows : n), dl, dd, dc, tz.overflow);
+    mark();
     B200_CUDA_OK(cudaGetLastError());
     uint32_t ov = 0;
     B200_CUDA_OK(cudaMemcpyAsync(&ov, tz.overflow, 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
+    if (prof && pn == 5) {
+        float t[4];
+        for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], pe[i], pe[i + 1]);
+        std::vector<uint32_t> cc(nq);
+        cudaMemcpy(cc.data(), tz.cand_cnt, nq * 4, cudaMemcpyDeviceToHost);
+        size_t tot = 0, mx = 0;
+        for (uint32_t v : cc) { tot += v; mx = std::max<size_t>(mx, v); }
+        fprintf(stderr, "[b200bf profile] nq %zu: pass1 %.3f ms, kth %.3f ms, pass2 %.3f ms, rerank %.3f ms; candidates/query "
+                        "%.0f (max %zu, cap %zu)\n", nq, t[0], t[1], t[2], t[3], (double)tot / nq, mx, cap_c);
+    }
+    for (int i = 0; i < pn; i++) cudaEventDestroy(pe[i]);
     stats.kernel_launches += 8;
     if (getenv("B200HNSW_BF_STATS")) {  // diagnostic: candidates generated per batch (costs a D2H copy)
         std::vector<uint32_t> c(nq);

@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(kBfThreads) bf_scan_kernel(const float4 *__res
                                                              uint32_t d4, uint32_t lane_chunks, uint32_t dim,
                                                              const float *__restrict__ Q, uint32_t nq, uint32_t k,
                                                              uint32_t rows_per_slice, float *__restrict__ part_d,
-                                                             uint64_t *__restrict__ part_l) {
+                                                             uint64_t *__restrict__ part_l,
+                                                             const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const BfSmem L(k);
     float *sQ = (float *)(smem + L.off_q);
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(kBfThreads) bf_scan_kernel(const float4 *__res
             for (int half = 0; half < 2; half++) {
                 const int r = lane + half * 32;
                 const uint32_t g = r0 + r;
-                const bool valid = g < r_end;
+                // mask: the caller's BaseFilterFunctor verdict per row (bruteforce.h:114,121); null = no filter
+                const bool valid = g < r_end && (!mask || mask[g]);
                 const float d = valid ? dt[qq * (kBfRT + 1) + r] : 0.f;
                 uint64_t lab = 0;
                 bool pend = valid && (cnt < (int)k || d <= wd);
@@ -208,7 +210,7 @@ __global__ void bf_pad_rows_kernel(const float *__restrict__ X, uint32_t dim, ui
 BruteIndex::~BruteIndex() {
     tz.release();
     cudaFree(dX); cudaFree(dLabels); cudaFree(dQ); cudaFree(dOutL); cudaFree(dOutD); cudaFree(dPartL);
-    cudaFree(dPartD); cudaFree(dPart2L); cudaFree(dPart2D); cudaFree(dCounts);
+    cudaFree(dPartD); cudaFree(dPart2L); cudaFree(dPart2D); cudaFree(dCounts); cudaFree(dMask);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -374,7 +376,7 @@ int BruteIndex::search_device(const float *dQ_, size_t nq, size_t k, uint64_t *d
     // measured on 1M x 768 (scripts/bench_bruteforce.py): streaming wins up to 8 queries, the tensor path (one 256-query
     // tile, ~1.4 ms) from there on; on small indexes its fixed cost (a dozen launches) is not worth it
     const bool tensor_pays = (double)n * (double)nq >= 6.7e7 || (nq > 8 && n >= 131072);
-    if (!want_scan && !want_stream && k <= n && (want_tensor || tensor_pays)) {
+    if (!want_scan && !want_stream && k <= (cur_mask ? cur_mask_rows : n) && (want_tensor || tensor_pays)) {
         const int rc = search_tensor(dQ_, nq, k, dl, dd, dc, st);
         if (rc <= 0) { last_path = 1; return rc; }  // done, or a real error; rc == 1 -> fall through to the scan
     }
@@ -421,27 +423,49 @@ int BruteIndex::search_scan(const float *dQ_, size_t nq, size_t k, uint64_t *dl,
         bf_scan_kernel<0><<<grid, kBfThreads, L.total, st>>>(dX, dLabels, (uint32_t)n, (uint32_t)d4,
                                                              (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_,
                                                              (uint32_t)nq, (uint32_t)k, (uint32_t)rows_per_slice,
-                                                             dPartD, dPartL);
+                                                             dPartD, dPartL, cur_mask);
     else
         bf_scan_kernel<1><<<grid, kBfThreads, L.total, st>>>(dX, dLabels, (uint32_t)n, (uint32_t)d4,
                                                              (uint32_t)(lane_floats / 4), (uint32_t)dim, dQ_,
                                                              (uint32_t)nq, (uint32_t)k, (uint32_t)rows_per_slice,
-                                                             dPartD, dPartL);
+                                                             dPartD, dPartL, cur_mask);
     B200_CUDA_OK(cudaGetLastError());
     rc = ensure_part2(merge_tree_scratch(slices, nq, k));
     if (rc) return rc;
     unsigned merges = 0;
     B200_CUDA_OK(merge_tree(dPartL, dPartD, slices, nq, k, dPart2L, dPart2D, dl, dd, st, &merges));
-    if (dc) bf_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(dc, (uint32_t)nq, (uint32_t)std::min(k, n));
+    if (dc)
+        bf_counts_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(dc, (uint32_t)nq,
+                                                                      (uint32_t)std::min(k, cur_mask ? cur_mask_rows : n));
     stats.kernel_launches += 1 + merges;
     return 0;
 }
 
-int BruteIndex::search_host(const float *Q, size_t nq, size_t k, uint64_t *labels, float *dists, uint32_t *counts) {
+int BruteIndex::search_host(const float *Q, size_t nq, size_t k, uint64_t *labels, float *dists, uint32_t *counts,
+                            const uint8_t *allowed) {
     if (nq == 0) return 0;
     if (!Q || !labels || !dists || k == 0) { set_error("search: null pointer or k == 0"); return B200HNSW_E_ARG; }
     std::lock_guard<std::mutex> g(mu);
     B200_CUDA_OK(cudaSetDevice(device));
+    struct MaskScope {  // the row mask of a filtered call lives exactly as long as the call
+        BruteIndex &ix;
+        ~MaskScope() { ix.cur_mask = nullptr; ix.cur_mask_rows = 0; }
+    } mask_scope{*this};
+    if (allowed) {
+        const size_t n = host.cur;
+        if (mask_cap < std::max<size_t>(n, 1)) {
+            cudaFree(dMask);
+            dMask = nullptr;
+            mask_cap = 0;
+            B200_CUDA_OK(cudaMalloc(&dMask, std::max<size_t>(cap, 1)));
+            mask_cap = std::max<size_t>(cap, 1);
+        }
+        size_t rows = 0;
+        for (size_t i = 0; i < n; i++) rows += allowed[i] ? 1 : 0;
+        if (n) B200_CUDA_OK(cudaMemcpyAsync(dMask, allowed, n, cudaMemcpyHostToDevice, stream));
+        cur_mask = dMask;
+        cur_mask_rows = rows;
+    }
     if (nq > scratch_q || k > scratch_k) {
         const size_t q = std::max(nq, scratch_q), kk = std::max(k, scratch_k);
         cudaFree(dQ); cudaFree(dOutL); cudaFree(dOutD); cudaFree(dCounts);

@@ -36,6 +36,11 @@ struct BruteIndex {
     std::mutex mu;
     b200hnsw_stats stats{};
     BruteTensor tz;
+    // row mask of the filtered search in progress (BaseFilterFunctor verdicts, bruteforce.h:114,121); null otherwise
+    uint8_t *dMask = nullptr;
+    size_t mask_cap = 0;
+    const uint8_t *cur_mask = nullptr;
+    size_t cur_mask_rows = 0;
     int last_path = 0;  // 0 = tiled exact scan, 1 = tensor-core candidates + exact re-rank, 2 = streaming exact scan
     // scratch
     float *dQ = nullptr;
@@ -55,7 +60,8 @@ struct BruteIndex {
     int remove(uint64_t label);
     int ensure_part(size_t elems);
     int search_device(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);
-    int search_host(const float *Q, size_t nq, size_t k, uint64_t *labels, float *dists, uint32_t *counts);
+    int search_host(const float *Q, size_t nq, size_t k, uint64_t *labels, float *dists, uint32_t *counts,
+                    const uint8_t *allowed = nullptr);
     // bf_tensor.cu
     int tensor_sync_rows(size_t first, size_t count);
     int search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *dl, float *dd, uint32_t *dc, cudaStream_t st);

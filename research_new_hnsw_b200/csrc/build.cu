@@ -35,6 +35,12 @@ namespace b200 {
 
 // ---- host side ---------------------------------------------------------------------------------------------
 
+BuildProfile *build_profile() {
+    static BuildProfile prof;
+    static const bool on = getenv("B200HNSW_BUILD_PROFILE") && atoi(getenv("B200HNSW_BUILD_PROFILE")) != 0;
+    return on ? &prof : nullptr;
+}
+
 static size_t env_size(const char *name, size_t dflt) {
     if (const char *e = getenv(name)) {
         const long long v = atoll(e);
@@ -45,7 +51,11 @@ static size_t env_size(const char *name, size_t dflt) {
 
 // addPoint staging (hnswalg.h:1153-1211,1255-1265): everything that does not need a distance.
 int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted) {
-    std::lock_guard<std::mutex> g(mu);
+    std::unique_lock<std::shared_mutex> g(rw);
+    struct StagedFlag {  // whatever path leaves this function, has_staged reflects the host image
+        HnswIndex &ix;
+        ~StagedFlag() { ix.has_staged = ix.linked < ix.host.cur; }
+    } staged_flag{*this};
     HostImage &m = host;
     std::vector<uint32_t> updates, revived;  // revived: slots that were marked deleted until this call
     for (size_t i = 0; i < n; i++) {
@@ -223,7 +233,10 @@ int HnswIndex::relink_points(std::vector<uint32_t> ids, const std::vector<uint32
             rc = B200HNSW_E_CUDA;
         }
     }
-    stats.kernel_launches += launches;
+    {
+        std::lock_guard<std::mutex> sg(stats_mu);
+        stats.kernel_launches += launches;
+    }
     mirror_dirty = true;
     return rc;
 }
@@ -322,6 +335,10 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
         }
     }
     a.flags = nb ? dev.flags : nullptr;
+    {
+        static const int pf_env = getenv("B200HNSW_BUILD_PF") ? atoi(getenv("B200HNSW_BUILD_PF")) : -1;
+        a.pf = pf_env >= 0 ? (uint32_t)pf_env : (kPfRows | kPfGreedy | kPfRound1);
+    }
     const size_t bufcap = nb ? 2 * m.efc : m.efc;
     // construction searches evaluate ~40 * efc nodes; a table of ~32 * efc slots is rebuilt about once in four searches
     // and lets twice as many CTAs share an SM as the no-rebuild size (measured: -30 % build time, same graph)
@@ -345,7 +362,16 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
 
 // Link every staged point (ids [linked, host.cur)) into the device graph.
 int HnswIndex::flush() {
-    std::lock_guard<std::mutex> g(mu);
+    if (!has_staged) return 0;  // the common case of a search: nothing staged, no exclusive lock
+    std::unique_lock<std::shared_mutex> g(rw);
+    return flush_locked();
+}
+
+int HnswIndex::flush_locked() {
+    struct StagedFlag {
+        HnswIndex &ix;
+        ~StagedFlag() { ix.has_staged = ix.linked < ix.host.cur; }
+    } staged_flag{*this};
     HostImage &m = host;
     if (linked >= m.cur) return 0;
     B200_CUDA_OK(cudaSetDevice(dev.device));
@@ -496,10 +522,24 @@ int HnswIndex::flush() {
     if (rc == 0) {
         B200_CUDA_OK(cudaEventRecord(e1, stream));
         B200_CUDA_OK(cudaStreamSynchronize(stream));
+        if (BuildProfile *prof = build_profile()) {
+            float t[3] = {0, 0, 0};
+            for (size_t i = 0; i + 3 < prof->ev.size(); i += 4)
+                for (int kx = 0; kx < 3; kx++) {
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, prof->ev[i + kx], prof->ev[i + kx + 1]);
+                    t[kx] += ms;
+                }
+            fprintf(stderr, "[b200hnsw build profile] %zu batches: search %.1f ms, link %.1f ms, reverse %.1f ms\n",
+                    prof->ev.size() / 4, t[0], t[1], t[2]);
+            for (cudaEvent_t e : prof->ev) cudaEventDestroy(e);
+            prof->ev.clear();
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         unsigned long long w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         B200_CUDA_OK(cudaMemcpy(w, bld.work, 64, cudaMemcpyDeviceToHost));
+        std::lock_guard<std::mutex> sg(stats_mu);
         stats.queries = n_new;
         stats.dist_evals = w[0]; stats.hops_base = w[1]; stats.hops_upper = w[2]; stats.visited_resets = w[3];
         stats.dropped_reverse_edges = w[4];

@@ -3,6 +3,7 @@
 // (build_insert.cu, build_update.cu, build_nb.cu) so that they compile in parallel; build.cu holds the host logic.
 #pragma once
 #include <algorithm>
+#include <vector>
 
 #include "hnsw_index.cuh"
 
@@ -31,6 +32,7 @@ struct BuildArgs {
     // hnswalg.h:1075-1139); kept at the end so the insert-mode kernels see the layout they were tuned with
     const uint32_t *batch_ids;  // [batch] ids of the points of this batch (insert mode: first + b)
     const uint8_t *flags;       // [n] delete marks; only read by the NB instantiations (elements marked deleted exist)
+    uint32_t pf;                // GraphView::pf of the construction searches (L2 prefetch policy)
 };
 
 // Implemented one family per translation unit (they compile in parallel): insert / update mode, and the same two with
@@ -41,6 +43,18 @@ int build_run_batch_update(int metric, const BuildArgs &a, size_t smem_search, s
 int build_run_batch_insert_nb(int metric, const BuildArgs &a, size_t smem_search, size_t smem_link, cudaStream_t st);
 int build_run_batch_update_nb(int metric, const BuildArgs &a, size_t smem_search, size_t smem_link, cudaStream_t st);
 int build_run_update_phase1(int metric, const BuildArgs &a, uint32_t *newlists, cudaStream_t st);
+
+// B200HNSW_BUILD_PROFILE=1: CUDA events around every build launch, summed per kernel by flush() (diagnostic only)
+struct BuildProfile {
+    std::vector<cudaEvent_t> ev;
+    void mark(cudaStream_t st) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    }
+};
+BuildProfile *build_profile();  // build.cu; nullptr unless profiling is on
 
 template <int LPV, int CPL>
 __device__ __forceinline__ void load_row(float4 (&v)[CPL], const float4 *row, uint32_t d4, int sub) {
@@ -62,6 +76,7 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
     TeamCtx c;
     c.bind(smem, L, s_ints, p.hash_bits);
     GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
+    g.pf = p.pf;
 
     const int tid = threadIdx.x;
     const int sub = tid % LPV, grp = tid / LPV;
@@ -343,11 +358,17 @@ static int run_batch(const BuildArgs &a, size_t smem_search, size_t smem_link, c
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
+    BuildProfile *prof = build_profile();
+    if (prof) prof->mark(st);
     build_search_kernel<LPV, CPL, METRIC, UPD, NB><<<a.batch, kTeam, smem_search, st>>>(a);
+    if (prof) prof->mark(st);
     build_link_kernel<LPV, CPL, METRIC, UPD><<<a.lists, kTeam, smem_link, st>>>(a);
-    // at most M lists are touched per (point, level); the grid is sized for the GPU, not for that bound
-    const unsigned rev_grid = (unsigned)std::min<size_t>((size_t)a.lists * a.M, (size_t)148 * 8);
+    if (prof) prof->mark(st);
+    // at most M lists are touched per (point, level); the grid is sized for the GPU (16 resident CTAs per SM), not for
+    // that bound
+    const unsigned rev_grid = (unsigned)std::min<size_t>((size_t)a.lists * a.M, (size_t)148 * 16);
     build_reverse_kernel<LPV, CPL, METRIC, UPD><<<rev_grid, kTeam, smem_link, st>>>(a);
+    if (prof) prof->mark(st);
     B200_CUDA_OK(cudaMemsetAsync(a.aff_count, 0, 4, st));
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -1,13 +1,14 @@
 // capi.cu -- extern "C" surface of libb200hnsw.so (include/b200hnsw.h).  No exception crosses this boundary.
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <shared_mutex>
 #include <string>
 
 #include "bruteforce.cuh"
 #include "hnsw_index.cuh"
 #include "merge_launch.cuh"
 
-struct b200hnsw_index { b200::HnswIndex ix; };
 struct b200bf_index { b200::BruteIndex ix; };
 
 namespace b200 {
@@ -104,7 +105,8 @@ int b200hnsw_load(const char *path, const b200hnsw_params *params, b200hnsw_inde
 int b200hnsw_save(b200hnsw_index *h, const char *path) {
     B200_GUARD_BEGIN
     if (!h || !path) { set_error("null argument"); return B200HNSW_E_ARG; }
-    int rc = h->ix.flush();
+    std::unique_lock<std::shared_mutex> lk(h->ix.rw);
+    int rc = h->ix.flush_locked();
     if (!rc) rc = h->ix.sync_host_mirror();
     if (rc) return rc;
     if (h->ix.host.save(path)) { set_error("Cannot open file"); return B200HNSW_E_OPEN; }
@@ -149,8 +151,6 @@ int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k
                           float *dists_out, uint32_t *counts_out, uint32_t *work_out) {
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
-    int rc = h->ix.flush();
-    if (rc) return rc;
     if (nq == 1 && Q && labels_out && dists_out && k)  // one query per call: coalesce concurrent callers into one launch
         return h->ix.search_coalesced(Q, k, ef, labels_out, dists_out, counts_out, work_out);
     return h->ix.search_host(Q, nq, k, ef, labels_out, dists_out, counts_out, work_out);
@@ -161,14 +161,13 @@ int b200hnsw_search_batch_filtered(b200hnsw_index *h, const float *Q, size_t nq,
                                    const uint8_t *allowed, uint64_t *labels_out, float *dists_out, uint32_t *counts_out) {
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
-    int rc = h->ix.flush();
-    if (rc) return rc;
     return h->ix.search_host(Q, nq, k, ef, labels_out, dists_out, counts_out, nullptr, allowed);
     B200_GUARD_END
 }
 
 int b200hnsw_get_labels(b200hnsw_index *h, uint64_t *labels_out, size_t capacity) {
     if (!h || !labels_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     const b200::HostImage &m = h->ix.host;
     if (capacity < m.cur) { set_error("labels_out is smaller than cur_element_count"); return B200HNSW_E_ARG; }
     for (size_t i = 0; i < m.cur; i++) labels_out[i] = m.label(i);
@@ -180,15 +179,14 @@ int b200hnsw_search_batch_device(b200hnsw_index *h, const float *dQ, size_t nq, 
                                  uint32_t *d_work_out, void *cuda_stream) {
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
-    int rc = h->ix.flush();
-    if (rc) return rc;
-    return h->ix.launch_search(dQ, nq, k, ef, d_labels_out, d_dists_out, d_counts_out, d_work_out,
+    return h->ix.search_device(dQ, nq, k, ef, d_labels_out, d_dists_out, d_counts_out, d_work_out,
                                (cudaStream_t)cuda_stream);
     B200_GUARD_END
 }
 
 int b200hnsw_get_info(b200hnsw_index *h, b200hnsw_info *o) {
     if (!h || !o) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     const b200::HostImage &m = h->ix.host;
     memset(o, 0, sizeof(*o));
     o->cur_element_count = m.cur; o->max_elements = m.max_elements; o->num_deleted = m.num_deleted;
@@ -209,9 +207,14 @@ int b200hnsw_get_levels(b200hnsw_index *h, const int32_t **levels_out) {
 int b200hnsw_get_linklist(b200hnsw_index *h, uint32_t id, int level, const uint32_t **ptr_out) {
     B200_GUARD_BEGIN
     if (!h || !ptr_out) { set_error("null argument"); return B200HNSW_E_ARG; }
-    int rc = h->ix.flush();
-    if (!rc) rc = h->ix.sync_host_mirror();
-    if (rc) return rc;
+    int rc = 0;
+    if (h->ix.has_staged || h->ix.mirror_dirty) {  // refresh the host mirror; otherwise a shared lock is enough
+        std::unique_lock<std::shared_mutex> xl(h->ix.rw);
+        rc = h->ix.flush_locked();
+        if (!rc) rc = h->ix.sync_host_mirror();
+        if (rc) return rc;
+    }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     const b200::HostImage &m = h->ix.host;
     if (id >= m.cur || level < 0 || level > m.levels[id]) { set_error("no such link list"); return B200HNSW_E_ARG; }
     *ptr_out = m.list(id, level);
@@ -221,6 +224,7 @@ int b200hnsw_get_linklist(b200hnsw_index *h, uint32_t id, int level, const uint3
 
 int b200hnsw_get_label(b200hnsw_index *h, uint32_t id, uint64_t *label_out) {
     if (!h || !label_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     if (id >= h->ix.host.cur) { set_error("internal id out of range"); return B200HNSW_E_ARG; }
     *label_out = h->ix.host.label(id);
     return 0;
@@ -228,6 +232,7 @@ int b200hnsw_get_label(b200hnsw_index *h, uint32_t id, uint64_t *label_out) {
 
 int b200hnsw_get_data(b200hnsw_index *h, uint32_t id, const float **vec_out) {
     if (!h || !vec_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     if (id >= h->ix.host.cur) { set_error("internal id out of range"); return B200HNSW_E_ARG; }
     *vec_out = h->ix.host.vec(id);
     return 0;
@@ -236,6 +241,7 @@ int b200hnsw_get_data(b200hnsw_index *h, uint32_t id, const float **vec_out) {
 int b200hnsw_get_data_by_label(b200hnsw_index *h, uint64_t label, float *vec_out) {
     B200_GUARD_BEGIN
     if (!h || !vec_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     const b200::HostImage &m = h->ix.host;
     auto it = m.label_lookup.find(label);
     if (it == m.label_lookup.end() || m.deleted(it->second)) { set_error("Label not found"); return B200HNSW_E_LABEL; }
@@ -247,6 +253,7 @@ int b200hnsw_get_data_by_label(b200hnsw_index *h, uint64_t label, float *vec_out
 int b200hnsw_mark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:853-883
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    std::unique_lock<std::shared_mutex> lk(h->ix.rw);
     b200::HostImage &m = h->ix.host;
     auto it = m.label_lookup.find(label);
     if (it == m.label_lookup.end()) { set_error("Label not found"); return B200HNSW_E_LABEL; }
@@ -262,6 +269,7 @@ int b200hnsw_mark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:853-
 int b200hnsw_unmark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:892-917
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    std::unique_lock<std::shared_mutex> lk(h->ix.rw);
     b200::HostImage &m = h->ix.host;
     auto it = m.label_lookup.find(label);
     if (it == m.label_lookup.end()) { set_error("Label not found"); return B200HNSW_E_LABEL; }
@@ -277,11 +285,12 @@ int b200hnsw_unmark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:89
 int b200hnsw_resize(b200hnsw_index *h, size_t new_max) {  // hnswalg.h:633-656
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    std::unique_lock<std::shared_mutex> lk(h->ix.rw);
     if (new_max < h->ix.host.cur) {
         set_error("Cannot resize, max element is less than the current number of elements");
         return B200HNSW_E_ARG;
     }
-    int rc = h->ix.flush();
+    int rc = h->ix.flush_locked();
     if (!rc) rc = h->ix.sync_host_mirror();
     if (rc) return rc;
     if (!h->ix.host.resize(new_max)) {
@@ -296,12 +305,14 @@ int b200hnsw_resize(b200hnsw_index *h, size_t new_max) {  // hnswalg.h:633-656
 
 int b200hnsw_index_file_size(b200hnsw_index *h, uint64_t *bytes_out) {
     if (!h || !bytes_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::shared_lock<std::shared_mutex> lk(h->ix.rw);
     *bytes_out = h->ix.host.file_size();
     return 0;
 }
 
 int b200hnsw_get_stats(b200hnsw_index *h, b200hnsw_stats *out) {
     if (!h || !out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::lock_guard<std::mutex> sg(h->ix.stats_mu);
     *out = h->ix.stats;
     return 0;
 }
@@ -393,6 +404,24 @@ int b200bf_search_batch(b200bf_index *h, const float *Q, size_t nq, size_t k, ui
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
     return h->ix.search_host(Q, nq, k, labels_out, dists_out, counts_out);
     B200_GUARD_END
+}
+
+/* searchKnn with a BaseFilterFunctor (bruteforce.h:106-135, filter at :114 and :121) */
+int b200bf_search_batch_filtered(b200bf_index *h, const float *Q, size_t nq, size_t k, const uint8_t *allowed,
+                                 uint64_t *labels_out, float *dists_out, uint32_t *counts_out) {
+    B200_GUARD_BEGIN
+    if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    return h->ix.search_host(Q, nq, k, labels_out, dists_out, counts_out, allowed);
+    B200_GUARD_END
+}
+
+int b200bf_get_labels(b200bf_index *h, uint64_t *labels_out, size_t capacity) {
+    if (!h || !labels_out) { set_error("null argument"); return B200HNSW_E_ARG; }
+    std::lock_guard<std::mutex> g(h->ix.mu);
+    const size_t n = h->ix.host.cur;
+    if (capacity < n) { set_error("labels_out is smaller than the element count"); return B200HNSW_E_ARG; }
+    for (size_t i = 0; i < n; i++) labels_out[i] = h->ix.host.label(i);
+    return 0;
 }
 
 int b200bf_search_batch_device(b200bf_index *h, const float *dQ, size_t nq, size_t k, uint64_t *d_labels_out,

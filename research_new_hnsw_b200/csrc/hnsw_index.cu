@@ -9,18 +9,72 @@
 
 namespace b200 {
 
-HnswIndex::~HnswIndex() {
-    if (dev.cap || dev.err_flag) {
-        cudaSetDevice(dev.device);
-        dev.release();
-        bld.release();
-    }
+SearchCtx::~SearchCtx() {
     cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (ev2) cudaEventDestroy(ev2);
     if (stream) cudaStreamDestroy(stream);
     if (stream2) cudaStreamDestroy(stream2);
+}
+
+int SearchCtx::ensure(size_t nq, size_t k, size_t dim) {
+    if (!stream) {
+        B200_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        B200_CUDA_OK(cudaEventCreate(&ev0));
+        B200_CUDA_OK(cudaEventCreate(&ev1));
+    }
+    if (nq <= scratch_q && k <= scratch_k) return 0;
+    const size_t q = std::max(nq, scratch_q), kk = std::max(k, scratch_k);
+    cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
+    dQ = nullptr; dLabels = nullptr; dDists = nullptr; dCounts = dWork = nullptr;
+    scratch_q = scratch_k = 0;
+    B200_CUDA_OK(cudaMalloc(&dQ, q * dim * 4));
+    B200_CUDA_OK(cudaMalloc(&dLabels, q * kk * 8));
+    B200_CUDA_OK(cudaMalloc(&dDists, q * kk * 4));
+    B200_CUDA_OK(cudaMalloc(&dCounts, q * 4));
+    B200_CUDA_OK(cudaMalloc(&dWork, q * 16));
+    scratch_q = q;
+    scratch_k = kk;
+    return 0;
+}
+
+// A free context, or a new one while the pool is below its size (B200HNSW_SEARCH_CTXS, default 4), else wait.
+SearchCtx *HnswIndex::acquire_ctx() {
+    static const size_t max_ctx = [] {
+        const char *e = getenv("B200HNSW_SEARCH_CTXS");
+        const int v = e ? atoi(e) : 4;
+        return (size_t)std::min(16, std::max(1, v));
+    }();
+    std::unique_lock<std::mutex> lk(ctx_mu);
+    for (;;) {
+        for (auto &c : ctxs)
+            if (!c->busy) { c->busy = true; return c.get(); }
+        if (ctxs.size() < max_ctx) {
+            ctxs.emplace_back(new SearchCtx());
+            ctxs.back()->busy = true;
+            return ctxs.back().get();
+        }
+        ctx_cv.wait(lk);
+    }
+}
+
+void HnswIndex::release_ctx(SearchCtx *c) {
+    {
+        std::lock_guard<std::mutex> lk(ctx_mu);
+        c->busy = false;
+    }
+    ctx_cv.notify_one();
+}
+
+HnswIndex::~HnswIndex() {
+    if (dev.cap || dev.err_flag) {
+        cudaSetDevice(dev.device);
+        dev.release();
+        bld.release();
+    }
+    ctxs.clear();
+    if (stream) cudaStreamDestroy(stream);
 }
 
 int HnswIndex::init_device() {
@@ -39,8 +93,6 @@ int HnswIndex::init_device() {
     dev.device = d;
     B200_CUDA_OK(cudaSetDevice(d));
     B200_CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    B200_CUDA_OK(cudaEventCreate(&ev0));
-    B200_CUDA_OK(cudaEventCreate(&ev1));
     return 0;
 }
 
@@ -185,22 +237,6 @@ int HnswIndex::upload_flags(const uint8_t *allowed, const uint32_t *extra, size_
     return 0;
 }
 
-int HnswIndex::ensure_scratch(size_t nq, size_t k) {
-    if (nq <= scratch_q && k <= scratch_k) return 0;
-    const size_t q = std::max(nq, scratch_q), kk = std::max(k, scratch_k);
-    cudaFree(dQ); cudaFree(dLabels); cudaFree(dDists); cudaFree(dCounts); cudaFree(dWork);
-    dQ = nullptr; dLabels = nullptr; dDists = nullptr; dCounts = dWork = nullptr;
-    scratch_q = scratch_k = 0;
-    B200_CUDA_OK(cudaMalloc(&dQ, q * host.dim * 4));
-    B200_CUDA_OK(cudaMalloc(&dLabels, q * kk * 8));
-    B200_CUDA_OK(cudaMalloc(&dDists, q * kk * 4));
-    B200_CUDA_OK(cudaMalloc(&dCounts, q * 4));
-    B200_CUDA_OK(cudaMalloc(&dWork, q * 16));
-    scratch_q = q;
-    scratch_k = kk;
-    return 0;
-}
-
 // Visited-table size.  128-thread teams (8 resident queries per SM): large enough that a typical query at this ef
 // never rebuilds it (D ~ 30*ef + 500 on the 1M x 128, M=32 graph).  Smaller teams trade table
 // size for resident queries: the table is rebuilt from the buffer at 5/8 load (re-evaluations only).
@@ -305,8 +341,11 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
             set_error("search with deleted elements supports at most 2^30 elements");
             return B200HNSW_E_UNSUPPORTED;
         }
-        int rc = upload_flags(allowed);
-        if (rc) return rc;
+        // `allowed` or dirty marks: the caller holds `rw` exclusively (search_host / search_device arrange that)
+        if (allowed || flags_dirty || !dev.flags) {
+            int rc = upload_flags(allowed);
+            if (rc) return rc;
+        }
     }
     if (linked == 0) {  // hnswalg.h:1273: empty index -> empty result
         B200_CUDA_OK(cudaMemsetAsync(dl, 0xFF, nq * k * 8, st));
@@ -336,14 +375,17 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.hash_bits = pick_hash_bits(a.bufcap, list_cap, team);
     {
         static const int pf_env = getenv("B200HNSW_PF") ? atoi(getenv("B200HNSW_PF")) : -1;
-        a.pf = pf_env >= 0 ? (uint32_t)pf_env : (kPfRows | kPfGreedy);
+        a.pf = pf_env >= 0 ? (uint32_t)pf_env : (kPfRows | kPfGreedy | kPfRound1);
     }
     const SearchSmem L(a.bufcap, (uint32_t)list_cap, a.d4, a.hash_bits);
     if (L.total > 226 * 1024) {
         set_error("search configuration needs more than 226 KB of shared memory");
         return B200HNSW_E_UNSUPPORTED;
     }
-    stats.kernel_launches += 1;
+    {
+        std::lock_guard<std::mutex> sg(stats_mu);
+        stats.kernel_launches += 1;
+    }
     if (nonbare)
         return prm.metric == B200HNSW_L2 ? launch_team<128, 0, true>(a, L.total, st) : launch_team<128, 1, true>(a, L.total, st);
     if (bf16) {
@@ -382,11 +424,9 @@ int HnswIndex::search_coalesced(const float *Q, size_t k, size_t ef_, uint64_t *
             continue;
         }
         co_leader = true;
-        lk.unlock();
-        // gather window: concurrent callers are typically microseconds apart
-        const auto t0 = std::chrono::steady_clock::now();
-        while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(co_window_us)) std::this_thread::yield();
-        lk.lock();
+        // gather window: concurrent callers are typically microseconds apart; sleep on the condition variable until the
+        // deadline instead of spinning (followers do not notify, a finished batch of another leader cannot exist here)
+        co_cv.wait_for(lk, std::chrono::microseconds(co_window_us));
         std::vector<Pending *> batch;
         for (auto it = co_queue.begin(); it != co_queue.end();) {
             if ((*it)->k == me.k && (*it)->ef == me.ef && batch.size() < 1024) {
@@ -398,13 +438,27 @@ int HnswIndex::search_coalesced(const float *Q, size_t k, size_t ef_, uint64_t *
         }
         lk.unlock();
         const size_t nb = batch.size(), d = host.dim;
-        std::vector<float> q(nb * d);
-        std::vector<uint64_t> l(nb * k);
-        std::vector<float> dd(nb * k);
-        std::vector<uint32_t> c(nb), w(nb * 4);
-        for (size_t i = 0; i < nb; i++) memcpy(q.data() + i * d, batch[i]->q, d * 4);
-        const int rc = search_host(q.data(), nb, k, ef_, l.data(), dd.data(), c.data(), w.data());
-        const std::string err = rc ? std::string(b200hnsw_last_error()) : std::string();
+        int rc = 0;
+        std::string err;
+        std::vector<uint64_t> l;
+        std::vector<float> dd;
+        std::vector<uint32_t> c, w;
+        try {  // whatever happens here, every request of the batch is completed and the leader role is released
+            std::vector<float> q(nb * d);
+            l.resize(nb * k);
+            dd.resize(nb * k);
+            c.resize(nb);
+            w.resize(nb * 4);
+            for (size_t i = 0; i < nb; i++) memcpy(q.data() + i * d, batch[i]->q, d * 4);
+            rc = search_host(q.data(), nb, k, ef_, l.data(), dd.data(), c.data(), w.data());
+            if (rc) err = b200hnsw_last_error();
+        } catch (const std::bad_alloc &) {
+            rc = B200HNSW_E_NOMEM;
+            err = "Not enough memory";
+        } catch (const std::exception &e) {
+            rc = B200HNSW_E_STATE;
+            err = std::string("internal error: ") + e.what();
+        }
         lk.lock();
         for (size_t i = 0; i < nb; i++) {
             Pending *p = batch[i];
@@ -428,6 +482,29 @@ int HnswIndex::search_coalesced(const float *Q, size_t k, size_t ef_, uint64_t *
     return me.rc;
 }
 
+// Shared lock for a search once the delete marks on the device are current; exclusive when they are not (they are
+// uploaded by launch_search) or when the call brings its own filter mask (the mask lives in the same device array).
+struct SearchLock {
+    std::shared_lock<std::shared_mutex> sh;
+    std::unique_lock<std::shared_mutex> ex;
+    SearchLock(HnswIndex &ix, bool filtered) {
+        if (!filtered) {
+            sh = std::shared_lock<std::shared_mutex>(ix.rw);
+            if (!(ix.host.num_deleted != 0 && (ix.flags_dirty || !ix.dev.flags))) return;
+            sh.unlock();
+        }
+        ex = std::unique_lock<std::shared_mutex>(ix.rw);
+    }
+};
+
+int HnswIndex::search_device(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
+                             uint32_t *dw, cudaStream_t st) {
+    int rc = flush();
+    if (rc) return rc;
+    SearchLock lock(*this, false);
+    return launch_search(dQ_, nq, k, ef_, dl, dd, dc, dw, st);
+}
+
 int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
                            uint32_t *counts, uint32_t *work, const uint8_t *allowed) {
     if (nq == 0) return 0;
@@ -435,9 +512,21 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
         set_error("search: null pointer or k == 0");
         return B200HNSW_E_ARG;
     }
-    std::lock_guard<std::mutex> g(mu);
+    int rc = flush();
+    if (rc) return rc;
+    SearchCtx *c = acquire_ctx();
+    {
+        SearchLock lock(*this, allowed != nullptr);
+        rc = search_host_locked(*c, Q, nq, k, ef_, labels, dists, counts, work, allowed);
+    }
+    release_ctx(c);
+    return rc;
+}
+
+int HnswIndex::search_host_locked(SearchCtx &c, const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels,
+                                  float *dists, uint32_t *counts, uint32_t *work, const uint8_t *allowed) {
     B200_CUDA_OK(cudaSetDevice(dev.device));
-    int rc = ensure_scratch(nq, k);
+    int rc = c.ensure(nq, k, host.dim);
     if (rc) return rc;
     // Large batches are cut into chunks that alternate between two streams, so the H2D copy of one chunk and the
     // D2H copy of the previous one overlap the kernel of the chunk in between (kernels of both streams share the SMs).
@@ -453,37 +542,38 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
     if (async_ok)
         if (const char *e = getenv("B200HNSW_CHUNKS")) chunks = (size_t)std::min(16, std::max(1, atoi(e)));
     const size_t per = (nq + chunks - 1) / chunks;
-    if (chunks > 1 && !stream2) {
-        B200_CUDA_OK(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
-        B200_CUDA_OK(cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+    if (chunks > 1 && !c.stream2) {
+        B200_CUDA_OK(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
+        B200_CUDA_OK(cudaEventCreateWithFlags(&c.ev2, cudaEventDisableTiming));
     }
     const size_t d = host.dim;
-    B200_CUDA_OK(cudaEventRecord(ev0, stream));
+    B200_CUDA_OK(cudaEventRecord(c.ev0, c.stream));
     if (chunks > 1) {  // the second stream starts after ev0 so the event pair brackets everything
-        B200_CUDA_OK(cudaStreamWaitEvent(stream2, ev0, 0));
+        B200_CUDA_OK(cudaStreamWaitEvent(c.stream2, c.ev0, 0));
     }
-    for (size_t c = 0; c < chunks; c++) {
-        const size_t off = c * per;
+    for (size_t ch = 0; ch < chunks; ch++) {
+        const size_t off = ch * per;
         if (off >= nq) break;
         const size_t n = std::min(per, nq - off);
-        cudaStream_t st = (c & 1) ? stream2 : stream;
-        B200_CUDA_OK(cudaMemcpyAsync(dQ + off * d, Q + off * d, n * d * 4, cudaMemcpyHostToDevice, st));
-        rc = launch_search(dQ + off * d, n, k, ef_, dLabels + off * k, dDists + off * k, dCounts + off, dWork + off * 4, st,
-                           allowed);
+        cudaStream_t st = (ch & 1) ? c.stream2 : c.stream;
+        B200_CUDA_OK(cudaMemcpyAsync(c.dQ + off * d, Q + off * d, n * d * 4, cudaMemcpyHostToDevice, st));
+        rc = launch_search(c.dQ + off * d, n, k, ef_, c.dLabels + off * k, c.dDists + off * k, c.dCounts + off,
+                           c.dWork + off * 4, st, allowed);
         if (rc) return rc;
-        B200_CUDA_OK(cudaMemcpyAsync(labels + off * k, dLabels + off * k, n * k * 8, cudaMemcpyDeviceToHost, st));
-        B200_CUDA_OK(cudaMemcpyAsync(dists + off * k, dDists + off * k, n * k * 4, cudaMemcpyDeviceToHost, st));
-        if (counts) B200_CUDA_OK(cudaMemcpyAsync(counts + off, dCounts + off, n * 4, cudaMemcpyDeviceToHost, st));
-        if (work) B200_CUDA_OK(cudaMemcpyAsync(work + off * 4, dWork + off * 4, n * 16, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(cudaMemcpyAsync(labels + off * k, c.dLabels + off * k, n * k * 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(cudaMemcpyAsync(dists + off * k, c.dDists + off * k, n * k * 4, cudaMemcpyDeviceToHost, st));
+        if (counts) B200_CUDA_OK(cudaMemcpyAsync(counts + off, c.dCounts + off, n * 4, cudaMemcpyDeviceToHost, st));
+        if (work) B200_CUDA_OK(cudaMemcpyAsync(work + off * 4, c.dWork + off * 4, n * 16, cudaMemcpyDeviceToHost, st));
     }
     if (chunks > 1) {
-        B200_CUDA_OK(cudaEventRecord(ev2, stream2));
-        B200_CUDA_OK(cudaStreamWaitEvent(stream, ev2, 0));
+        B200_CUDA_OK(cudaEventRecord(c.ev2, c.stream2));
+        B200_CUDA_OK(cudaStreamWaitEvent(c.stream, c.ev2, 0));
     }
-    B200_CUDA_OK(cudaEventRecord(ev1, stream));
-    B200_CUDA_OK(cudaStreamSynchronize(stream));
+    B200_CUDA_OK(cudaEventRecord(c.ev1, c.stream));
+    B200_CUDA_OK(cudaStreamSynchronize(c.stream));
     float ms = 0;
-    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+    std::lock_guard<std::mutex> sg(stats_mu);
     stats.last_kernel_ms = ms;  // kernel (+ overlapped copies when chunked)
     stats.queries = nq;
     stats.dist_evals = stats.hops_base = stats.hops_upper = stats.visited_resets = 0;

@@ -1,8 +1,11 @@
 // hnsw_index.cuh -- HierarchicalNSW<float> replacement: host mirror + HBM image + kernel dispatch.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <list>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -30,21 +33,9 @@ struct BuildScratch {
     void release();
 };
 
-struct HnswIndex {
-    b200hnsw_params prm{};
-    HostImage host;
-    DeviceIndex dev;
-    size_t ef = 10;  // hnswalg.h:115
-    std::mutex mu;   // serialises host-pointer calls that share the scratch buffers
-    b200hnsw_stats stats{};
-    // staged insertions (add_batch before flush): ids [linked, host.cur) are not yet in the graph
-    size_t linked = 0;
-    uint32_t dev_entry = (uint32_t)-1;  // entry point / max level of the linked part of the graph
-    int dev_maxlevel = -1;
-    bool mirror_dirty = false;          // device link lists are newer than the host mirror
-    bool flags_dirty = true;            // delete marks changed since the last upload
-    BuildScratch bld;
-    // scratch for the host-pointer search path
+// Device scratch + streams of ONE host-pointer search call.  Concurrent callers each take a context from a small pool, so
+// batch searches from several host threads overlap on the GPU instead of queueing behind one mutex.
+struct SearchCtx {
     float *dQ = nullptr;
     uint64_t *dLabels = nullptr;
     float *dDists = nullptr;
@@ -52,6 +43,37 @@ struct HnswIndex {
     size_t scratch_q = 0, scratch_k = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    bool busy = false;
+    ~SearchCtx();
+    int ensure(size_t nq, size_t k, size_t dim);
+};
+
+struct HnswIndex {
+    b200hnsw_params prm{};
+    HostImage host;
+    DeviceIndex dev;
+    size_t ef = 10;  // hnswalg.h:115
+    // Locking (the reference: label-op / link-list locks for writers, lock-free const searchKnn, hnswalg.h:40-43,59):
+    // every call that changes the host image, the device graph or the delete marks holds `rw` exclusively; searches and
+    // read-only accessors hold it shared.  C-ABI entry points take the lock; the *_locked / launch_* members assume it.
+    std::shared_mutex rw;
+    std::atomic<bool> has_staged{false};   // add_batch staged points that flush() has not linked yet
+    std::mutex stats_mu;
+    b200hnsw_stats stats{};
+    // staged insertions (add_batch before flush): ids [linked, host.cur) are not yet in the graph
+    size_t linked = 0;
+    uint32_t dev_entry = (uint32_t)-1;  // entry point / max level of the linked part of the graph
+    int dev_maxlevel = -1;
+    bool mirror_dirty = false;          // device link lists are newer than the host mirror
+    std::atomic<bool> flags_dirty{true};  // delete marks changed since the last upload
+    BuildScratch bld;
+    cudaStream_t stream = nullptr;      // build / update stream
+    // pool of search contexts (host-pointer search path)
+    std::mutex ctx_mu;
+    std::condition_variable ctx_cv;
+    std::vector<std::unique_ptr<SearchCtx>> ctxs;
+    SearchCtx *acquire_ctx();
+    void release_ctx(SearchCtx *c);
 
     // micro-batching of concurrent single-query calls
     struct Pending {
@@ -72,24 +94,30 @@ struct HnswIndex {
     int alloc_device(size_t cap);
     int upload_all();                       // host mirror -> HBM (after load)
     int upload_upper();                     // rebuild up_base / links_up from the host mirror
-    int ensure_scratch(size_t nq, size_t k);
     // extra: internal ids uploaded as deleted although the host image says live (relink_points)
     int upload_flags(const uint8_t *allowed = nullptr, const uint32_t *extra = nullptr, size_t n_extra = 0);
     bool revived_on_device = false;
     int sync_bf16(size_t first, size_t count);
+    // kernel launch only; the caller holds `rw` (shared is enough unless `allowed` is given or the marks are dirty)
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
                       uint32_t *dw, cudaStream_t st, const uint8_t *allowed = nullptr);
+    // entry points of the C ABI: link staged points, bring the delete marks up to date, take the lock, search
+    int search_device(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
+                      uint32_t *dw, cudaStream_t st);
     int search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
                     uint32_t *counts, uint32_t *work, const uint8_t *allowed = nullptr);
+    int search_host_locked(SearchCtx &c, const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
+                           uint32_t *counts, uint32_t *work, const uint8_t *allowed);
     // build.cu: addPoint staging and the batched GPU graph build
     int add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted = false);
     size_t replace_scan = 0;  // where the search for a deleted slot resumes (replace_deleted)
-    int flush();
+    int flush();              // takes `rw` exclusively when there is something to link
+    int flush_locked();       // caller holds `rw` exclusively
     // build.cu: scratch + batch-independent kernel arguments (args is a BuildArgs*)
     int prepare_build(void *args, size_t max_batch, size_t *max_lists, size_t *smem_search, size_t *smem_link);
-    // build.cu: updatePoint for ids that are already linked (vectors in the host image are the new ones); mu held
+    // build.cu: updatePoint for ids that are already linked (vectors in the host image are the new ones); rw held
     int relink_points(std::vector<uint32_t> ids, const std::vector<uint32_t> &revived = {});
-    int sync_host_mirror();
+    int sync_host_mirror();   // caller holds `rw` exclusively
 };
 
 uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team = 128);
@@ -97,3 +125,6 @@ int pick_team(size_t nq);
 void fill_pad_rows(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k, cudaStream_t st);
 
 }  // namespace b200
+
+// the opaque handle of include/b200hnsw.h
+struct b200hnsw_index { b200::HnswIndex ix; };

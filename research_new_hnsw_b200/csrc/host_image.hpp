@@ -205,6 +205,11 @@ struct HostBrute {
         data.assign(n * row, 0);
         lookup.clear();
     }
+    uint64_t label(size_t i) const {  // bruteforce.h:51-52,81-82: the label sits behind the vector
+        uint64_t l;
+        memcpy(&l, data.data() + i * row + dim * 4, 8);
+        return l;
+    }
     int save(const char *path) const {  // bruteforce.h:138-149
         FILE *f = fopen(path, "wb");
         if (!f) return -1;

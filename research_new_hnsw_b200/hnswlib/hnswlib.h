@@ -51,7 +51,8 @@ class BaseFilterFunctor {
     virtual ~BaseFilterFunctor() {}
 };
 
-// hnswlib.h:134-150 (kept for source compatibility; stop conditions are host callbacks and are not supported)
+// hnswlib.h:134-150.  Stop conditions are host callbacks; the GPU engine runs the ones that declare a device formulation
+// through the non-reference hook at the end (stop_condition.h).
 template <typename dist_t>
 class BaseSearchStopCondition {
  public:
@@ -61,6 +62,8 @@ class BaseSearchStopCondition {
     virtual bool should_consider_candidate(dist_t candidate_dist, dist_t lowerBound) = 0;
     virtual bool should_remove_extra() = 0;
     virtual void filter_results(std::vector<std::pair<dist_t, labeltype>> &candidates) = 0;
+    // true: "the max_candidates closest elements, cut at distance epsilon" describes this condition's result
+    virtual bool b200_epsilon_form(float *epsilon, size_t *max_candidates) const { return false; }
     virtual ~BaseSearchStopCondition() {}
 };
 
@@ -294,14 +297,24 @@ class BruteforceSearch : public AlgorithmInterface<dist_t> {
     }
     std::priority_queue<std::pair<dist_t, labeltype>> searchKnn(const void *query_data, size_t k,
                                                                 BaseFilterFunctor *isIdAllowed = nullptr) const {
-        if (isIdAllowed)
-            throw std::runtime_error("BaseFilterFunctor host callbacks are not supported by the GPU engine");
         std::priority_queue<std::pair<dist_t, labeltype>> res;
         if (cur_element_count == 0 || k == 0) return res;
         std::vector<uint64_t> labels(k);
         std::vector<float> dists(k);
         uint32_t cnt = 0;
-        b200detail::check(b200bf_search_batch(h_, (const float *)query_data, 1, k, labels.data(), dists.data(), &cnt));
+        if (isIdAllowed) {
+            // bruteforce.h:114,121: rows the functor rejects are skipped.  The functor is a host callback: it is evaluated
+            // once per stored row, the scan kernels take the verdicts as a row mask.
+            const size_t n = cur_element_count;
+            std::vector<uint64_t> all(n);
+            b200detail::check(b200bf_get_labels(h_, all.data(), n));
+            std::vector<uint8_t> allowed(n);
+            for (size_t i = 0; i < n; i++) allowed[i] = (*isIdAllowed)((labeltype)all[i]) ? 1 : 0;
+            b200detail::check(b200bf_search_batch_filtered(h_, (const float *)query_data, 1, k, allowed.data(), labels.data(),
+                                                           dists.data(), &cnt));
+        } else {
+            b200detail::check(b200bf_search_batch(h_, (const float *)query_data, 1, k, labels.data(), dists.data(), &cnt));
+        }
         for (uint32_t j = 0; j < cnt; j++) res.emplace(dists[j], (labeltype)labels[j]);
         return res;
     }
@@ -471,6 +484,7 @@ class HierarchicalNSW : public AlgorithmInterface<dist_t> {
         b200detail::check(b200hnsw_get_levels(h_, &lv));
         element_levels_.assign(max_elements_, 0);
         for (size_t i = 0; i < cur_element_count; i++) element_levels_[i] = lv[i];
+        levels_mirrored_ = cur_element_count;
     }
 
     template <typename data_t>
@@ -520,11 +534,19 @@ class HierarchicalNSW : public AlgorithmInterface<dist_t> {
         if (isIdAllowed) {
             // the functor is a host callback: evaluate it once per stored label, the kernel treats "not allowed" like a
             // delete mark (hnswalg.h:406-407)
-            const size_t n = cur_element_count;
-            std::vector<uint64_t> all(n);
-            b200detail::check(b200hnsw_get_labels(h_, all.data(), n));
-            std::vector<uint8_t> allowed(n);
-            for (size_t i = 0; i < n; i++) allowed[i] = (*isIdAllowed)((labeltype)all[i]) ? 1 : 0;
+            // (the label of every internal id is cached until the next mutating call; the library skips the upload of a
+            // mask identical to the one it already holds, so repeated calls with the same functor pay only the callbacks)
+            std::vector<uint8_t> allowed;
+            {
+                std::lock_guard<std::mutex> g(fields_mu_);
+                const size_t n = cur_element_count;
+                if (filter_labels_.size() != n) {
+                    filter_labels_.resize(n);
+                    b200detail::check(b200hnsw_get_labels(h_, filter_labels_.data(), n));
+                }
+                allowed.resize(n);
+                for (size_t i = 0; i < n; i++) allowed[i] = (*isIdAllowed)((labeltype)filter_labels_[i]) ? 1 : 0;
+            }
             b200detail::check(b200hnsw_search_batch_filtered(h_, (const float *)query_data, 1, k, 0, allowed.data(),
                                                              labels.data(), dists.data(), &cnt));
             for (uint32_t j = 0; j < cnt; j++) result.emplace(dists[j], (labeltype)labels[j]);
@@ -537,6 +559,42 @@ class HierarchicalNSW : public AlgorithmInterface<dist_t> {
         for (uint32_t j = 0; j < cnt; j++) result.emplace(dists[j], (labeltype)labels[j]);
         return result;
     }
+    // hnswalg.h:1327-1378.  Only stop conditions with a device formulation run (stop_condition.h); the others throw.
+    std::vector<std::pair<dist_t, labeltype>> searchStopConditionClosest(const void *query_data,
+                                                                         BaseSearchStopCondition<dist_t> &stop_condition,
+                                                                         BaseFilterFunctor *isIdAllowed = nullptr) const {
+        std::vector<std::pair<dist_t, labeltype>> result;
+        if (cur_element_count == 0) return result;
+        float epsilon = 0.f;
+        size_t kmax = 0;
+        if (!stop_condition.b200_epsilon_form(&epsilon, &kmax))
+            throw std::runtime_error(
+                "searchStopConditionClosest: this stop condition is a host callback without a GPU formulation (only "
+                "EpsilonSearchStopCondition is supported; there is no CPU fallback)");
+        if (kmax == 0) return result;
+        auto top = [&]() {
+            // ef = k = max_num_candidates; searchKnn uses max(ef, k)
+            return isIdAllowed ? searchKnn(query_data, kmax, isIdAllowed) : searchKnn(query_data, kmax);
+        }();
+        result.resize(top.size());
+        size_t sz = top.size();
+        while (!top.empty()) {  // closest first, as the reference returns (:1369-1376)
+            result[--sz] = top.top();
+            top.pop();
+        }
+        stop_condition.filter_results(result);
+        return result;
+    }
+
+    // hnswalg.h:995-1072: new vector for an element that is already stored, both phases on the GPU (the
+    // updateNeighborProbability of the reference is 1.0 from every caller in the repository and is taken as 1.0 here).
+    void updatePoint(const void *dataPoint, tableint internalId, float updateNeighborProbability) {
+        (void)updateNeighborProbability;
+        uint64_t lab = getExternalLabel(internalId);
+        b200detail::check(b200hnsw_add_batch(h_, (const float *)dataPoint, &lab, 1));
+        after_add(1);
+    }
+
     // batched extension: one kernel launch for nq queries; rows closest-first, padded with label = SIZE_MAX
     void searchKnnBatch(const float *Q, size_t nq, size_t k, labeltype *labels_out, dist_t *dists_out,
                         uint32_t *counts_out = nullptr, size_t ef = 0) const {
@@ -600,13 +658,21 @@ class HierarchicalNSW : public AlgorithmInterface<dist_t> {
         offsetLevel0_ = 0;
         label_offset_ = o.label_offset;
     }
-    void after_add(size_t n) {
-        const size_t before = cur_element_count;
+    // Parallel addPoint callers (the reference allows them, hnswalg.h:40-43): whoever gets here copies every level that
+    // has not been mirrored yet, so no window between "count before" and "count after" can lose one.
+    mutable std::mutex fields_mu_;
+    size_t levels_mirrored_ = 0;
+    mutable std::vector<uint64_t> filter_labels_;  // getExternalLabel of every internal id, for filter functors
+    void after_add(size_t) {
+        std::lock_guard<std::mutex> g(fields_mu_);
+        filter_labels_.clear();
         sync_fields();
         const int32_t *lv = nullptr;
         b200detail::check(b200hnsw_get_levels(h_, &lv));
         if (element_levels_.size() < max_elements_) element_levels_.resize(max_elements_, 0);
-        for (size_t i = before; i < before + n && i < cur_element_count; i++) element_levels_[i] = lv[i];
+        const size_t cur = cur_element_count;
+        for (size_t i = levels_mirrored_; i < cur; i++) element_levels_[i] = lv[i];
+        if (cur > levels_mirrored_) levels_mirrored_ = cur;
     }
 };
 

@@ -149,3 +149,31 @@ def test_partial_merge_tree_many_slices(lib, orc, monkeypatch):
     rt, rc2 = g.searchKnnBatch(Q[:5], k2), c.search(Q[:5], k2)
     assert g.stats()["hops_base"] == 2
     assert np.array_equal(rt["labels"], rc2["labels"]) and np.array_equal(rt["dists"], rc2["dists"])
+
+
+@pytest.mark.parametrize("path,n,d,k,nq", [("scan", 6000, 48, 10, 70), ("stream", 20000, 100, 7, 5), ("tensor", 40000, 128, 20, 300)])
+def test_filter_functor_is_a_row_mask_in_every_path(lib, orc, monkeypatch, path, n, d, k, nq):
+    """searchKnn(query, k, isIdAllowed) (bruteforce.h:106-135, filter at :114 and :121): rows whose label the functor
+    rejects are skipped.  Equal to an unfiltered search over an index that holds only the allowed rows -- ids and
+    distances bit-identical -- on the tiled scan, the streaming scan and the tcgen05 path."""
+    monkeypatch.setenv("B200HNSW_BF_PATH", path)
+    X = bind.lowrank_data(n, d, seed=71, latent=16, noise=0.2)
+    Q = bind.lowrank_data(nq, d, seed=72, latent=16, noise=0.2)
+    labels = np.arange(n, dtype=np.uint64) * 5 + 3
+    allowed = lambda l: l % 3 != 0
+    g = lib.BruteforceSearch(lib.L2Space(d), n)
+    g.addPoints(X, labels)
+    r = g.searchKnnFiltered(Q, k, allowed)
+    assert g.stats()["hops_base"] == {"scan": 0, "tensor": 1, "stream": 2}[path]
+    keep = np.array([allowed(int(l)) for l in labels])
+    c = orc.bf_new(bind.L2, d, int(keep.sum()))
+    c.add(X[keep], labels[keep])
+    rc = c.search(Q, k)
+    assert np.array_equal(r["labels"], rc["labels"]) and np.array_equal(r["dists"], rc["dists"])
+    assert (r["counts"] == k).all()
+    r0 = g.searchKnnBatch(Q, k)                                  # the mask does not outlive its call
+    c0 = orc.bf_new(bind.L2, d, n)
+    c0.add(X, labels)
+    assert np.array_equal(r0["labels"], c0.search(Q, k)["labels"])
+    few = g.searchKnnFiltered(Q[:3], k, lambda l: l < 3 + 5 * 4)  # fewer allowed rows than k: padded result
+    assert (few["counts"] == 4).all() and (few["labels"][:, 4:] == np.uint64(2**64 - 1)).all()

