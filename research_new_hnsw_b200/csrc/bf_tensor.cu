@@ -45,7 +45,9 @@ constexpr int kGThreads = 192;
 constexpr uint32_t kStageA = kGM * kGK * 2;   // 16 KB
 constexpr uint32_t kStageB = kGN * kGK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageA + kStageB;
-constexpr uint32_t kGemmSmem = kGStages * kStageBytes + 1024 /*align*/ + 8192 /*barriers + per-tile tables*/;
+constexpr int kQCap = 512;     // entries of one epilogue warp's hit queue (pass 2)
+constexpr uint32_t kGemmSmem = kGStages * kStageBytes + 1024 /*align*/ + 8192 /*barriers + per-tile tables*/ +
+                               4 * 2 * kQCap * 4 /*hit queues*/;
 constexpr float kErrC = 0.0078125f + 0.000244140625f;   // 2^-7 + 2^-12
 constexpr float kErrDelta = 4e-6f;
 
@@ -97,6 +99,20 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGN >> 3) << 17) | ((uint32_t)(kGM >> 4) << 24);
+
+// Hit queue of one epilogue warp: entries (column of the tile << 8 | row of the tile, value), all of the CURRENT tile.
+// 32 entries per step: their atomicAdds on the per-query counters are in flight together.
+__device__ __forceinline__ void flush_queue(const GemmArgs &a, const uint32_t *qmeta, const float *qval, uint32_t qn,
+                                            uint32_t p, uint32_t t, int lane) {
+    __syncwarp();
+    for (uint32_t e = lane; e < qn; e += 32) {
+        const uint32_t m = qmeta[e];
+        const uint32_t q = t * kGN + (m >> 8), r = p * kGM + (m & 0xFFu);
+        const uint32_t pos = atomicAdd(a.cand_cnt + q, 1u);
+        if (pos < a.cap) a.cand[(size_t)q * a.cap + pos] = make_uint2(r, __float_as_uint(qval[e]));
+    }
+    __syncwarp();
+}
 
 template <int METRIC, int MODE>
 __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -181,6 +197,9 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         float *s_B = (float *)(tail + 256);          // [2][kGN]
         float *s_T = s_B + 2 * kGN;                  // [2][kGN]
         uint32_t *s_min = (uint32_t *)(s_T + 2 * kGN);  // [2][kGN] (pass 1)
+        uint32_t *qmeta = s_min + 2 * kGN + (warp - 2) * 2 * kQCap;  // this warp's hit queue (pass 2): [kQCap] meta
+        float *qval = (float *)(qmeta + kQCap);                       // [kQCap] key - E (without the per-query constant)
+        uint32_t qn = 0;
         constexpr float alpha = METRIC == 1 ? -1.f : -2.f;
         uint32_t buf = 0, bphase = 0, tb = 0;
         float pB[2], pT[2];
@@ -263,24 +282,57 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
                         hits |= (w <= Tc[j] + rhs_r) ? (1u << j) : 0u;
                     }
                     if (!rvalid) hits = 0;
-                    uint32_t any = __reduce_or_sync(0xffffffffu, hits);
-                    while (any) {  // rare: columns with at least one admitted row
-                        const int j = __ffs(any) - 1;
-                        any &= any - 1;
-                        const uint32_t q = t * kGN + c * 32 + j;
-                        const bool hit = (hits >> j) & 1u;
-                        const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                        uint32_t base = 0;
-                        if (lane == 0) base = atomicAdd(a.cand_cnt + q, (uint32_t)__popc(m));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (hit) {
-                            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                            if (pos < a.cap) {
+                    if (__any_sync(0xffffffffu, hits != 0)) {
+                        // Hits go to this warp's shared-memory queue (no global round trip on the epilogue's critical
+                        // path: one atomicAdd per hit column cost ~1 us each, more than the tile's whole mainloop);
+                        // the queue is flushed 32 entries at a time, their atomics in flight together.
+                        uint32_t mine = (uint32_t)__popc(hits), incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += up;
+                        }
+                        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                        if (qn + total > (uint32_t)kQCap) {
+                            flush_queue(a, qmeta, qval, qn, p, t, lane);
+                            qn = 0;
+                        }
+                        if (total <= (uint32_t)kQCap) {
+                            uint32_t pos = qn + incl - mine;
+                            uint32_t hb = hits;
+                            while (hb) {
+                                const int j = __ffs(hb) - 1;
+                                hb &= hb - 1;
                                 uint32_t vj = 0;  // v[] lives in registers: select, do not index
 #pragma unroll
                                 for (int jj = 0; jj < 32; jj++) vj = jj == j ? v[jj] : vj;
                                 const float wj = fmaf(B[c * 32 + j], bx, alpha * __uint_as_float(vj));
-                                a.cand[(size_t)q * a.cap + pos] = make_uint2(r, __float_as_uint(wj + Ar));
+                                qmeta[pos] = ((uint32_t)(c * 32 + j) << 8) | (uint32_t)(quarter * 32 + lane);
+                                qval[pos] = wj + Ar;
+                                pos++;
+                            }
+                            qn += total;
+                        } else {  // a chunk with more hits than the queue holds (degenerate data): direct path
+                            uint32_t any = __reduce_or_sync(0xffffffffu, hits);
+                            while (any) {
+                                const int j = __ffs(any) - 1;
+                                any &= any - 1;
+                                const uint32_t q = t * kGN + c * 32 + j;
+                                const bool hit = (hits >> j) & 1u;
+                                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                                uint32_t base = 0;
+                                if (lane == 0) base = atomicAdd(a.cand_cnt + q, (uint32_t)__popc(m));
+                                base = __shfl_sync(0xffffffffu, base, 0);
+                                if (hit) {
+                                    const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                                    if (pos < a.cap) {
+                                        uint32_t vj = 0;
+#pragma unroll
+                                        for (int jj = 0; jj < 32; jj++) vj = jj == j ? v[jj] : vj;
+                                        const float wj = fmaf(B[c * 32 + j], bx, alpha * __uint_as_float(vj));
+                                        a.cand[(size_t)q * a.cap + pos] = make_uint2(r, __float_as_uint(wj + Ar));
+                                    }
+                                }
                             }
                         }
                     }
@@ -289,6 +341,10 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             tc_fence_before();
             if (lane == 0) mbar_arrive(tempty + buf);  // this warp is done with the accumulator
             if (++buf == 2) { buf = 0; bphase ^= 1; }
+            if (MODE == 1 && qn) {  // the queue's entries are relative to this tile: emptied before the next one
+                flush_queue(a, qmeta, qval, qn, p, t, lane);
+                qn = 0;
+            }
             if (nit < items) {
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
@@ -412,8 +468,9 @@ __global__ void __launch_bounds__(256) bf_kth_smem_kernel(const uint32_t *__rest
 //     through shared memory 32 floats at a time so global reads stay coalesced while every thread sums ITS
 //     candidate strictly in index order; then the k smallest (dist, label) by rank, closest first.
 constexpr int kRrThreads = 256;
-constexpr int kRrRows = 128;   // survivor rows staged per round of step C
-constexpr int kRrStride = 33;  // floats per staged row (+1: conflict-free column walks)
+constexpr int kRrRows = 64;     // survivor rows staged per round of step C (4 threads per row)
+constexpr int kRrChunk4 = 32;   // 128-bit chunks of every row per stage (512 bytes)
+constexpr int kRrStride = 132;  // floats per staged row (stride = 4 mod 32 banks: the 8 rows x 4 lanes of a warp differ)
 
 template <int METRIC>
 __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
@@ -496,61 +553,79 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     const uint32_t ns = s_cnt;  // <= cnt <= cap words fit in tile[] (sized max(kRrRows*kRrStride, cap))
     for (uint32_t i = tid; i < ns; i += kRrThreads) ids[i] = surv[i];
     __syncthreads();
-    // the rows of the first round are on their way to L2 while the first stage is set up
-    for (uint32_t i = tid; i < min(ns, (uint32_t)kRrRows) * ((d4 * 16 + 127) / 128); i += kRrThreads) {
+    // every survivor row is on its way to L2 while the first stage is set up
+    {
         const uint32_t lpr = (d4 * 16 + 127) / 128;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(X + (size_t)ids[i / lpr] * d4) + (i % lpr) * 128));
+        for (uint32_t i = tid; i < ns * lpr; i += kRrThreads)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(X + (size_t)ids[i / lpr] * d4) + (i % lpr) * 128));
     }
     // ---- C: exact distances of the survivors in reference order ----
+    // kRrRows rows per round, 128 floats of every row per stage (coalesced 512-byte reads, 8 independent 128-bit loads per
+    // thread in flight); thread (row, l) owns the reference's lane accumulator l of its row -- elements 4j + l in index
+    // order -- and thread (row, 0) the sequential tail; ((s0+s1)+s2)+s3 + tail is formed over the four lanes at the end.
+    const uint32_t rl = (uint32_t)tid >> 2, al = (uint32_t)tid & 3;
     for (uint32_t base = 0; base < ns; base += kRrRows) {
         const uint32_t nb = min((uint32_t)kRrRows, ns - base);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, t = 0.f;
-        for (uint32_t c0 = 0; c0 < d4; c0 += 8) {  // 8 float4 = 32 floats = 128 bytes per row and stage
-            __syncthreads();
+        float acc = 0.f, t = 0.f;
+        for (uint32_t c0 = 0; c0 < d4; c0 += kRrChunk4) {
+            float4 v[kRrRows * kRrChunk4 / kRrThreads];
 #pragma unroll
-            for (int i = 0; i < kRrRows * 8 / kRrThreads; i++) {
-                const uint32_t f = tid + kRrThreads * i;  // float4 slot: candidate f/8, part f%8
-                const uint32_t cj = f >> 3, part = f & 7;
-                if (cj < nb) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (c0 + part < d4) v = __ldg(X + (size_t)ids[base + cj] * d4 + c0 + part);
-                    float *dst = tile + cj * kRrStride + part * 4;
-                    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-                }
+            for (int i = 0; i < kRrRows * kRrChunk4 / kRrThreads; i++) {
+                const uint32_t f = tid + kRrThreads * i;  // float4 slot: row f / 32, part f % 32
+                const uint32_t cj = f / kRrChunk4, part = f % kRrChunk4;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cj < nb && c0 + part < d4) v[i] = __ldg(X + (size_t)ids[base + cj] * d4 + c0 + part);
+            }
+            __syncthreads();  // the previous stage has been consumed
+#pragma unroll
+            for (int i = 0; i < kRrRows * kRrChunk4 / kRrThreads; i++) {
+                const uint32_t f = tid + kRrThreads * i;
+                *(float4 *)(tile + (f / kRrChunk4) * kRrStride + (f % kRrChunk4) * 4) = v[i];
             }
             __syncthreads();
-            if ((uint32_t)tid < nb) {
-                const float *row = tile + tid * kRrStride;
-#pragma unroll
-                for (int part = 0; part < 8; part++) {
+            if (rl < nb) {
+                const float *row = tile + rl * kRrStride;
+                const uint32_t pend = min((uint32_t)kRrChunk4, d4 - c0);
+                for (uint32_t part = 0; part < pend; part++) {
                     const uint32_t c = c0 + part;
-                    if (c < d4) {
-                        const float4 qv = *(const float4 *)(qs + 4 * c);
-                        const float x0 = row[part * 4], x1 = row[part * 4 + 1], x2 = row[part * 4 + 2], x3 = row[part * 4 + 3];
-                        float m0, m1, m2, m3;
+                    if (c < lane_chunks) {
+                        const float x = row[part * 4 + al], qv = qs[4 * c + al];
+                        float m;
                         if (METRIC == 0) {
-                            const float a0 = __fsub_rn(qv.x, x0), a1 = __fsub_rn(qv.y, x1), a2 = __fsub_rn(qv.z, x2), a3 = __fsub_rn(qv.w, x3);
-                            m0 = __fmul_rn(a0, a0); m1 = __fmul_rn(a1, a1); m2 = __fmul_rn(a2, a2); m3 = __fmul_rn(a3, a3);
+                            const float a0 = __fsub_rn(qv, x);
+                            m = __fmul_rn(a0, a0);
                         } else {
-                            m0 = __fmul_rn(qv.x, x0); m1 = __fmul_rn(qv.y, x1); m2 = __fmul_rn(qv.z, x2); m3 = __fmul_rn(qv.w, x3);
+                            m = __fmul_rn(qv, x);
                         }
-                        if (c < lane_chunks) {
-                            s0 = __fadd_rn(s0, m0); s1 = __fadd_rn(s1, m1); s2 = __fadd_rn(s2, m2); s3 = __fadd_rn(s3, m3);
-                        } else {
-                            t = __fadd_rn(t, m0); t = __fadd_rn(t, m1); t = __fadd_rn(t, m2); t = __fadd_rn(t, m3);
+                        acc = __fadd_rn(acc, m);
+                    } else if (al == 0) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float x = row[part * 4 + e], qv = qs[4 * c + e];
+                            float m;
+                            if (METRIC == 0) {
+                                const float a0 = __fsub_rn(qv, x);
+                                m = __fmul_rn(a0, a0);
+                            } else {
+                                m = __fmul_rn(qv, x);
+                            }
+                            t = __fadd_rn(t, m);
                         }
                     }
                 }
             }
         }
-        __syncthreads();
-        if ((uint32_t)tid < nb) {
-            float r = __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
+        // the four lane accumulators of a row sit in four consecutive lanes
+        const float s1 = __shfl_down_sync(0xffffffffu, acc, 1), s2 = __shfl_down_sync(0xffffffffu, acc, 2),
+                    s3 = __shfl_down_sync(0xffffffffu, acc, 3);
+        if (rl < nb && al == 0) {
+            float r = __fadd_rn(__fadd_rn(__fadd_rn(acc, s1), s2), s3);
             r = __fadd_rn(r, t);
             if (METRIC == 1) r = __fsub_rn(1.0f, r);
-            fd[base + tid] = r;
-            cl[base + tid] = labels[ids[base + tid]];
+            fd[base + rl] = r;
+            cl[base + rl] = labels[ids[base + rl]];
         }
+        __syncthreads();
     }
     __syncthreads();
     for (uint32_t j = tid; j < k; j += kRrThreads) {  // padding for rows the ranks below do not fill
@@ -672,6 +747,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     size_t cap_c = std::max<size_t>(1536, 12 * k);
     if (const char *e = getenv("B200HNSW_BF_CAP")) cap_c = std::max(256, atoi(e));
     cap_c = std::max(cap_c, tz.cap_floor);
+    cap_c = (cap_c + 3) / 4 * 4;  // the re-rank kernel's shared arrays stay 16-byte aligned
     if (nq_pad > tz.q_cap || cap_c != tz.cap) {
         cudaFree(tz.qb); cudaFree(tz.qn2); cudaFree(tz.thr); cudaFree(tz.cand); cudaFree(tz.cand_cnt);
         tz.qb = nullptr; tz.qn2 = tz.thr = nullptr; tz.cand = tz.cand_cnt = nullptr; tz.q_cap = 0;

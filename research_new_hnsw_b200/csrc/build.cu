@@ -343,7 +343,7 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
     // construction searches evaluate ~40 * efc nodes; a table of ~32 * efc slots is rebuilt about once in four searches
     // and lets twice as many CTAs share an SM as the no-rebuild size (measured: -30 % build time, same graph)
     {
-        size_t want = std::min<size_t>(8192, 32 * m.efc + 1024);
+        size_t want = std::min<size_t>(env_size("B200HNSW_BUILD_HASH", 8192), 32 * m.efc + 1024);
         want = std::max(want, 8 * (bufcap + list_cap) / 3 + 64);  // a hop must fit above the 5/8 rebuild mark
         a.hash_bits = 10;
         while ((1ull << a.hash_bits) < want) a.hash_bits++;

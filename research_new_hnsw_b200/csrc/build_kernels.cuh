@@ -9,7 +9,10 @@
 
 namespace b200 {
 
-constexpr int kTeam = 128;      // threads per CTA of the build kernels
+#ifndef B200_BUILD_TEAM
+#define B200_BUILD_TEAM 128
+#endif
+constexpr int kTeam = B200_BUILD_TEAM;  // threads per CTA of the build kernels
 constexpr uint32_t kCapIn = 32;  // incoming reverse edges kept per list and batch
 
 struct BuildArgs {

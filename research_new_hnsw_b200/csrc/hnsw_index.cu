@@ -262,17 +262,17 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
     return bits;
 }
 
-template <int TEAM, int LPV, int CPL, int METRIC, bool NB, int STORE>
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB, int STORE, bool FULL>
 static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
     static bool configured[16] = {};  // per device; set once (benign race: idempotent)
     int d = 0;
     cudaGetDevice(&d);
     if (d < 16 && !configured[d]) {
         cudaFuncAttributes fa;
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE>));
+        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE, FULL>));
         int optin = 0;
         B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE>,
+        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE, FULL>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
@@ -290,23 +290,35 @@ static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
-    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE>, a));
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE, FULL>, a));
     return 0;
+}
+
+// Rows of exactly LPV * CPL chunks take the FULL instantiation on the throughput path (bare-bone search, f32 or bf16
+// rows, 64- and 128-thread teams); everything else the generic one.
+template <int TEAM, int LPV, int CPL, int METRIC, bool NB, int STORE>
+static int launch_shape(const SearchArgs &a, size_t smem, cudaStream_t st) {
+    static const bool full_on = !(getenv("B200HNSW_FULL") && atoi(getenv("B200HNSW_FULL")) == 0);
+    if constexpr (!NB && TEAM >= 64) {
+        if (full_on && a.d4 == (uint32_t)(LPV * CPL) && (STORE == 0 || a.d16 * 2 == a.d4))
+            return launch_one<TEAM, LPV, CPL, METRIC, NB, STORE, true>(a, smem, st);
+    }
+    return launch_one<TEAM, LPV, CPL, METRIC, NB, STORE, false>(a, smem, st);
 }
 
 template <int TEAM, int METRIC, bool NB = false, int STORE = 0>
 static int launch_team(const SearchArgs &a, size_t smem, cudaStream_t st) {
     const uint32_t d4 = a.d4;
-    if (d4 <= 8) return launch_one<TEAM, 8, 1, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 16) return launch_one<TEAM, 8, 2, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 24) return launch_one<TEAM, 8, 3, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 32) return launch_one<TEAM, 8, 4, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 48) return launch_one<TEAM, 16, 3, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 64) return launch_one<TEAM, 16, 4, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 96) return launch_one<TEAM, 32, 3, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 128) return launch_one<TEAM, 32, 4, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 192) return launch_one<TEAM, 32, 6, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 256) return launch_one<TEAM, 32, 8, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 8) return launch_shape<TEAM, 8, 1, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 16) return launch_shape<TEAM, 8, 2, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 24) return launch_shape<TEAM, 8, 3, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 32) return launch_shape<TEAM, 8, 4, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 48) return launch_shape<TEAM, 16, 3, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 64) return launch_shape<TEAM, 16, 4, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 96) return launch_shape<TEAM, 32, 3, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 128) return launch_shape<TEAM, 32, 4, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 192) return launch_shape<TEAM, 32, 6, METRIC, NB, STORE>(a, smem, st);
+    if (d4 <= 256) return launch_shape<TEAM, 32, 8, METRIC, NB, STORE>(a, smem, st);
     set_error("dimension > 1024 is not supported by the search kernel");
     return B200HNSW_E_UNSUPPORTED;
 }
@@ -537,7 +549,43 @@ int HnswIndex::search_host_locked(SearchCtx &c, const float *Q, size_t nq, size_
         if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
         return at.type == cudaMemoryTypeHost;
     };
-    const bool async_ok = !allowed && nq >= 4096 && pinned(Q) && pinned(labels) && pinned(dists) && pinned(counts) && pinned(work);
+    const bool all_pinned = pinned(Q) && pinned(labels) && pinned(dists) && pinned(counts) && pinned(work);
+    // Page-locked buffers are device-accessible under unified addressing: the kernel reads its query (d floats per CTA)
+    // and stores its k result rows straight over PCIe -- the copies are a few KB per query spread over the whole launch,
+    // so the call costs one kernel launch and nothing is staged.  (B200HNSW_ZEROCOPY=0: staged copies as below.)
+    static const bool zc_on = !(getenv("B200HNSW_ZEROCOPY") && atoi(getenv("B200HNSW_ZEROCOPY")) == 0);
+    if (zc_on && all_pinned && !allowed && nq >= 64) {
+        void *dq = nullptr, *dl = nullptr, *dd = nullptr, *dc = nullptr, *dw = nullptr;
+        bool ok = cudaHostGetDevicePointer(&dq, (void *)Q, 0) == cudaSuccess &&
+                  cudaHostGetDevicePointer(&dl, (void *)labels, 0) == cudaSuccess &&
+                  cudaHostGetDevicePointer(&dd, (void *)dists, 0) == cudaSuccess;
+        if (ok && counts) ok = cudaHostGetDevicePointer(&dc, (void *)counts, 0) == cudaSuccess;
+        if (ok && work) ok = cudaHostGetDevicePointer(&dw, (void *)work, 0) == cudaSuccess;
+        if (ok) {
+            B200_CUDA_OK(cudaEventRecord(c.ev0, c.stream));
+            rc = launch_search((const float *)dq, nq, k, ef_, (uint64_t *)dl, (float *)dd, (uint32_t *)dc, (uint32_t *)dw,
+                               c.stream);
+            if (rc) return rc;
+            B200_CUDA_OK(cudaEventRecord(c.ev1, c.stream));
+            B200_CUDA_OK(cudaStreamSynchronize(c.stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+            std::lock_guard<std::mutex> sg(stats_mu);
+            stats.last_kernel_ms = ms;
+            stats.queries = nq;
+            stats.dist_evals = stats.hops_base = stats.hops_upper = stats.visited_resets = 0;
+            if (work)
+                for (size_t i = 0; i < nq; i++) {
+                    stats.dist_evals += work[i * 4 + 0];
+                    stats.hops_base += work[i * 4 + 1];
+                    stats.hops_upper += work[i * 4 + 2];
+                    stats.visited_resets += work[i * 4 + 3];
+                }
+            return 0;
+        }
+        cudaGetLastError();  // not mappable after all: staged copies
+    }
+    const bool async_ok = !allowed && nq >= 4096 && all_pinned;
     size_t chunks = async_ok ? 3 : 1;  // measured: 3 chunks beat 2 and 4+ (smaller kernels lose more to their tails)
     if (async_ok)
         if (const char *e = getenv("B200HNSW_CHUNKS")) chunks = (size_t)std::min(16, std::max(1, atoi(e)));
