@@ -603,15 +603,20 @@ def run_b200(a, rank, local_rank, world):
     if world == 1:
         for e in (16, 32, 48, 64, 96, 128, 192, 256):
             rec_e = recall_at_k(sweep_fn(Qs, e), gt)
-            dev_search(dbatches[0], a.nq, e)
-            torch.cuda.synchronize()
-            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record()
-            for s in range(3):
+            for s in range(2):
                 dev_search(dbatches[s % len(dbatches)], a.nq, e)
-            t1e.record()
             torch.cuda.synchronize()
-            ef_table.append({"ef": e, "recall_at_10": round(rec_e, 4), "qps": 3 * a.nq / (t0e.elapsed_time(t1e) * 1e-3)})
+            best = None
+            for rep in range(2):  # best of two short runs: a 3-launch timing is exposed to a single host hiccup
+                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0e.record()
+                for s in range(4):
+                    dev_search(dbatches[s % len(dbatches)], a.nq, e)
+                t1e.record()
+                torch.cuda.synchronize()
+                ms_e = t0e.elapsed_time(t1e) / 4
+                best = ms_e if best is None else min(best, ms_e)
+            ef_table.append({"ef": e, "recall_at_10": round(rec_e, 4), "qps": a.nq / (best * 1e-3)})
 
     # ---- end to end through the host-pointer C ABI: pinned host buffers, H2D + kernel + D2H inside the timed region
     hq = [torch.from_numpy(b).pin_memory() for b in batches]

@@ -211,6 +211,7 @@ int HnswIndex::relink_points(std::vector<uint32_t> ids, const std::vector<uint32
         scatter_rows_kernel<<<(unsigned)((B * 32 + 127) / 128), 128, 0, stream>>>(
             (const float4 *)bld.stage_rows, bld.stage_labels, bld.batch_ids, (uint32_t)B, (uint32_t)dev.d4, (uint32_t)dev.d16,
             dev.vec, dev.labels, prm.storage == B200HNSW_BF16 ? dev.vec16 : nullptr, nb ? dev.flags : nullptr);
+        if (nb) flags_on_device_valid = false;  // the kernel clears marks on the device
         launches += 1;
         b0 += B;
         if (linked <= 1) continue;  // a single element has nothing to connect to (hnswalg.h:1001-1003)

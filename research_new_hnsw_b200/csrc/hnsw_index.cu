@@ -5,7 +5,7 @@
 #include <cstring>
 #include <thread>
 
-#include "hnsw_index.cuh"
+#include "search_launch.cuh"
 
 namespace b200 {
 
@@ -227,12 +227,32 @@ int HnswIndex::upload_all() {
 int HnswIndex::upload_flags(const uint8_t *allowed, const uint32_t *extra, size_t n_extra) {
     if (!flags_dirty && dev.flags && !allowed && !n_extra) return 0;
     B200_CUDA_OK(cudaSetDevice(dev.device));
-    if (!dev.flags) B200_CUDA_OK(cudaMalloc(&dev.flags, std::max<size_t>(dev.cap, 1)));
+    if (!dev.flags) {
+        B200_CUDA_OK(cudaMalloc(&dev.flags, std::max<size_t>(dev.cap, 1)));
+        flags_on_device_valid = false;
+    }
     std::vector<uint8_t> f(host.cur);
     for (size_t i = 0; i < host.cur; i++) f[i] = (host.deleted(i) || (allowed && !allowed[i])) ? 1 : 0;
     for (size_t i = 0; i < n_extra; i++)
         if (extra[i] < host.cur) f[extra[i]] = 1;
-    if (host.cur) B200_CUDA_OK(cudaMemcpy(dev.flags, f.data(), host.cur, cudaMemcpyHostToDevice));
+    // calls that pass the same filter over and over (the shim evaluates a functor into the same verdicts each time) do
+    // not pay the upload again: the device array is only rewritten when its content changes
+    uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)host.cur;
+    {
+        size_t i = 0;
+        for (; i + 8 <= f.size(); i += 8) {
+            uint64_t w;
+            memcpy(&w, f.data() + i, 8);
+            h = (h ^ w) * 0x100000001b3ull;
+            h ^= h >> 29;
+        }
+        for (; i < f.size(); i++) h = (h ^ f[i]) * 0x100000001b3ull;
+    }
+    if (!(flags_on_device_valid && h == flags_on_device_hash)) {
+        if (host.cur) B200_CUDA_OK(cudaMemcpy(dev.flags, f.data(), host.cur, cudaMemcpyHostToDevice));
+        flags_on_device_hash = h;
+        flags_on_device_valid = true;
+    }
     flags_dirty = allowed != nullptr || n_extra != 0;  // a per-call state must not outlive its call
     return 0;
 }
@@ -260,74 +280,6 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
     uint32_t bits = 10;
     while ((1ull << bits) < want) bits++;
     return bits;
-}
-
-template <int TEAM, int LPV, int CPL, int METRIC, bool NB, int STORE, bool FULL>
-static int launch_one(const SearchArgs &a, size_t smem, cudaStream_t st) {
-    static bool configured[16] = {};  // per device; set once (benign race: idempotent)
-    int d = 0;
-    cudaGetDevice(&d);
-    if (d < 16 && !configured[d]) {
-        cudaFuncAttributes fa;
-        B200_CUDA_OK(cudaFuncGetAttributes(&fa, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE, FULL>));
-        int optin = 0;
-        B200_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d));
-        B200_CUDA_OK(cudaFuncSetAttribute(hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE, FULL>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          optin - (int)fa.sharedSizeBytes));
-        configured[d] = true;
-    }
-    // programmatic stream serialization: this grid may start while the previous kernel of the stream drains (the kernel
-    // orders its own output writes behind the previous grid with griddepcontrol.wait)
-    static const bool pdl = !(getenv("B200HNSW_PDL") && atoi(getenv("B200HNSW_PDL")) == 0);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(a.nq);
-    cfg.blockDim = dim3(TEAM);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, hnsw_search_kernel<TEAM, LPV, CPL, METRIC, NB, STORE, FULL>, a));
-    return 0;
-}
-
-// Rows of exactly LPV * CPL chunks take the FULL instantiation on the throughput path (bare-bone search, f32 or bf16
-// rows, 64- and 128-thread teams); everything else the generic one.
-template <int TEAM, int LPV, int CPL, int METRIC, bool NB, int STORE>
-static int launch_shape(const SearchArgs &a, size_t smem, cudaStream_t st) {
-    static const bool full_on = !(getenv("B200HNSW_FULL") && atoi(getenv("B200HNSW_FULL")) == 0);
-    if constexpr (!NB && TEAM >= 64) {
-        if (full_on && a.d4 == (uint32_t)(LPV * CPL) && (STORE == 0 || a.d16 * 2 == a.d4))
-            return launch_one<TEAM, LPV, CPL, METRIC, NB, STORE, true>(a, smem, st);
-    }
-    return launch_one<TEAM, LPV, CPL, METRIC, NB, STORE, false>(a, smem, st);
-}
-
-template <int TEAM, int METRIC, bool NB = false, int STORE = 0>
-static int launch_team(const SearchArgs &a, size_t smem, cudaStream_t st) {
-    const uint32_t d4 = a.d4;
-    if (d4 <= 8) return launch_shape<TEAM, 8, 1, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 16) return launch_shape<TEAM, 8, 2, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 24) return launch_shape<TEAM, 8, 3, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 32) return launch_shape<TEAM, 8, 4, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 48) return launch_shape<TEAM, 16, 3, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 64) return launch_shape<TEAM, 16, 4, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 96) return launch_shape<TEAM, 32, 3, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 128) return launch_shape<TEAM, 32, 4, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 192) return launch_shape<TEAM, 32, 6, METRIC, NB, STORE>(a, smem, st);
-    if (d4 <= 256) return launch_shape<TEAM, 32, 8, METRIC, NB, STORE>(a, smem, st);
-    set_error("dimension > 1024 is not supported by the search kernel");
-    return B200HNSW_E_UNSUPPORTED;
-}
-
-template <int METRIC>
-static int launch_metric(const SearchArgs &a, size_t smem, int team, cudaStream_t st) {
-    if (team == 32) return launch_team<32, METRIC>(a, smem, st);
-    if (team == 64) return launch_team<64, METRIC>(a, smem, st);
-    return launch_team<128, METRIC>(a, smem, st);
 }
 
 // Team size: a batch that cannot fill the GPU with 64-thread teams is latency-bound -> 128 threads per query.
@@ -398,14 +350,10 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
         std::lock_guard<std::mutex> sg(stats_mu);
         stats.kernel_launches += 1;
     }
-    if (nonbare)
-        return prm.metric == B200HNSW_L2 ? launch_team<128, 0, true>(a, L.total, st) : launch_team<128, 1, true>(a, L.total, st);
-    if (bf16) {
-        if (team == 64)
-            return prm.metric == B200HNSW_L2 ? launch_team<64, 0, false, 1>(a, L.total, st) : launch_team<64, 1, false, 1>(a, L.total, st);
-        return prm.metric == B200HNSW_L2 ? launch_team<128, 0, false, 1>(a, L.total, st) : launch_team<128, 1, false, 1>(a, L.total, st);
-    }
-    return prm.metric == B200HNSW_L2 ? launch_metric<0>(a, L.total, team, st) : launch_metric<1>(a, L.total, team, st);
+    const bool l2 = prm.metric == B200HNSW_L2;
+    if (nonbare) return l2 ? search_launch_l2_var(a, L.total, 1, st) : search_launch_ip_var(a, L.total, 1, st);
+    if (bf16) return l2 ? search_launch_l2_var(a, L.total, team == 64 ? 2 : 3, st) : search_launch_ip_var(a, L.total, team == 64 ? 2 : 3, st);
+    return l2 ? search_launch_l2_bare(a, L.total, team, st) : search_launch_ip_bare(a, L.total, team, st);
 }
 
 __global__ void fill_pad_kernel(float *dd, uint32_t *dc, uint32_t *dw, size_t nq, size_t k) {

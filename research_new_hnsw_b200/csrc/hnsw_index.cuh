@@ -97,6 +97,8 @@ struct HnswIndex {
     // extra: internal ids uploaded as deleted although the host image says live (relink_points)
     int upload_flags(const uint8_t *allowed = nullptr, const uint32_t *extra = nullptr, size_t n_extra = 0);
     bool revived_on_device = false;
+    uint64_t flags_on_device_hash = 0;   // content hash of dev.flags as last uploaded
+    bool flags_on_device_valid = false;  // false after anything else wrote dev.flags (scatter_rows_kernel) or reallocated it
     int sync_bf16(size_t first, size_t count);
     // kernel launch only; the caller holds `rw` (shared is enough unless `allowed` is given or the marks are dirty)
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
