@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmArgs a) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment (SWIZZLE_128B) as an OFFSET into the shared array: casting through an integer would lose the
+    // address space and turn every table / queue access of the epilogue into a generic load
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *tail = smem + kGStages * kStageBytes;
     uint64_t *full = (uint64_t *)tail;            // [kGStages]
     uint64_t *empty = full + kGStages;            // [kGStages]
@@ -200,6 +202,9 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         uint32_t *qmeta = s_min + 2 * kGN + (warp - 2) * 2 * kQCap;  // this warp's hit queue (pass 2): [kQCap] meta
         float *qval = (float *)(qmeta + kQCap);                       // [kQCap] key - E (without the per-query constant)
         uint32_t qn = 0;
+        uint32_t pend_q = 0, pend_r = 0, pend_pos = 0;  // this lane's queue entry whose counter atomic is in flight
+        float pend_v = 0.f;
+        bool pend = false;
         constexpr float alpha = METRIC == 1 ? -1.f : -2.f;
         uint32_t buf = 0, bphase = 0, tb = 0;
         float pB[2], pT[2];
@@ -341,9 +346,27 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             tc_fence_before();
             if (lane == 0) mbar_arrive(tempty + buf);  // this warp is done with the accumulator
             if (++buf == 2) { buf = 0; bphase ^= 1; }
-            if (MODE == 1 && qn) {  // the queue's entries are relative to this tile: emptied before the next one
-                flush_queue(a, qmeta, qval, qn, p, t, lane);
-                qn = 0;
+            if (MODE == 1) {
+                // The queue's entries are relative to this tile, so it is emptied before the next one -- but nobody has to
+                // wait for it: the counter atomics of the first 32 entries are ISSUED now, their candidate stores happen
+                // at the end of the next tile (the round trip hides behind that tile's chunks).  More than 32 hits per
+                // warp and tile are rare and go the synchronous way.
+                if (pend && pend_pos < a.cap) a.cand[(size_t)pend_q * a.cap + pend_pos] = make_uint2(pend_r, __float_as_uint(pend_v));
+                pend = false;
+                if (qn) {
+                    __syncwarp();
+                    if ((uint32_t)lane < qn) {
+                        const uint32_t m = qmeta[lane];
+                        pend_q = t * kGN + (m >> 8);
+                        pend_r = p * kGM + (m & 0xFFu);
+                        pend_v = qval[lane];
+                        pend_pos = atomicAdd(a.cand_cnt + pend_q, 1u);
+                        pend = true;
+                    }
+                    if (qn > 32) flush_queue(a, qmeta + 32, qval + 32, qn - 32, p, t, lane);
+                    __syncwarp();
+                    qn = 0;
+                }
             }
             if (nit < items) {
 #pragma unroll
@@ -363,6 +386,8 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
                 a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
             }
         }
+        if (MODE == 1 && pend && pend_pos < a.cap)
+            a.cand[(size_t)pend_q * a.cap + pend_pos] = make_uint2(pend_r, __float_as_uint(pend_v));
     }
     tc_fence_before();
     __syncthreads();
@@ -553,36 +578,40 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     const uint32_t ns = s_cnt;  // <= cnt <= cap words fit in tile[] (sized max(kRrRows*kRrStride, cap))
     for (uint32_t i = tid; i < ns; i += kRrThreads) ids[i] = surv[i];
     __syncthreads();
-    // every survivor row is on its way to L2 while the first stage is set up
-    {
-        const uint32_t lpr = (d4 * 16 + 127) / 128;
-        for (uint32_t i = tid; i < ns * lpr; i += kRrThreads)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char *)(X + (size_t)ids[i / lpr] * d4) + (i % lpr) * 128));
-    }
     // ---- C: exact distances of the survivors in reference order ----
     // kRrRows rows per round, 128 floats of every row per stage (coalesced 512-byte reads, 8 independent 128-bit loads per
     // thread in flight); thread (row, l) owns the reference's lane accumulator l of its row -- elements 4j + l in index
     // order -- and thread (row, 0) the sequential tail; ((s0+s1)+s2)+s3 + tail is formed over the four lanes at the end.
     const uint32_t rl = (uint32_t)tid >> 2, al = (uint32_t)tid & 3;
+    constexpr int kLd = kRrRows * kRrChunk4 / kRrThreads;  // 128-bit loads per thread and stage
+    // stage (base, c0) -> registers; the loads of the NEXT stage are issued before the current one is consumed, so their
+    // latency hides behind the arithmetic (ncu of the single-buffered version: 25 % of the samples on the staging stores
+    // waiting for their loads, and prefetching all survivor rows to L2 up front thrashed it: 1.65x the DRAM bytes)
+    float4 v[kLd];
+    auto issue = [&](uint32_t base, uint32_t c0) {
+        const uint32_t nbb = min((uint32_t)kRrRows, ns - base);
+#pragma unroll
+        for (int i = 0; i < kLd; i++) {
+            const uint32_t f = tid + kRrThreads * i;  // float4 slot: row f / 32, part f % 32
+            const uint32_t cj = f / kRrChunk4, part = f % kRrChunk4;
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cj < nbb && c0 + part < d4) v[i] = __ldg(X + (size_t)ids[base + cj] * d4 + c0 + part);
+        }
+    };
+    if (ns) issue(0, 0);
     for (uint32_t base = 0; base < ns; base += kRrRows) {
         const uint32_t nb = min((uint32_t)kRrRows, ns - base);
         float acc = 0.f, t = 0.f;
         for (uint32_t c0 = 0; c0 < d4; c0 += kRrChunk4) {
-            float4 v[kRrRows * kRrChunk4 / kRrThreads];
-#pragma unroll
-            for (int i = 0; i < kRrRows * kRrChunk4 / kRrThreads; i++) {
-                const uint32_t f = tid + kRrThreads * i;  // float4 slot: row f / 32, part f % 32
-                const uint32_t cj = f / kRrChunk4, part = f % kRrChunk4;
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cj < nb && c0 + part < d4) v[i] = __ldg(X + (size_t)ids[base + cj] * d4 + c0 + part);
-            }
             __syncthreads();  // the previous stage has been consumed
 #pragma unroll
-            for (int i = 0; i < kRrRows * kRrChunk4 / kRrThreads; i++) {
+            for (int i = 0; i < kLd; i++) {
                 const uint32_t f = tid + kRrThreads * i;
                 *(float4 *)(tile + (f / kRrChunk4) * kRrStride + (f % kRrChunk4) * 4) = v[i];
             }
             __syncthreads();
+            if (c0 + kRrChunk4 < d4) issue(base, c0 + kRrChunk4);
+            else if (base + kRrRows < ns) issue(base + kRrRows, 0);
             if (rl < nb) {
                 const float *row = tile + rl * kRrStride;
                 const uint32_t pend = min((uint32_t)kRrChunk4, d4 - c0);

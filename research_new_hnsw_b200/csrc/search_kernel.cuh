@@ -90,7 +90,9 @@ __device__ __forceinline__ float group_sum(float v, uint32_t gmask) {
 #endif
 constexpr uint32_t kPfLine = B200_PF_LINE;
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// rows ids[first..n) of `bytes` each, one thread per 128-byte line
+// rows ids[first..n) of `bytes` each, one thread per 128-byte line (consecutive threads take the consecutive lines of a
+// row).  One thread per ROW -- one id read and one address per row, four back-to-back prefetches -- executes fewer
+// instructions but measured 0.968 vs 0.809 ms per 10 k queries: 32 different rows per prefetch instruction.
 template <int TEAM>
 __device__ __forceinline__ void prefetch_rows(const char *base, uint32_t bytes, const uint32_t *ids, int first, int n) {
     const uint32_t lpr = (bytes + kPfLine - 1) / kPfLine;
