@@ -658,6 +658,30 @@ def run_b200(a, rank, local_rank, world):
                 if e is not None:
                     e.synchronize()
             torch.cuda.synchronize()
+    elif sw == 1 and not os.environ.get("B200HNSW_BENCH_SYNC_E2E"):
+        # serving loop over the asynchronous host-pointer C ABI (b200hnsw_search_batch_submit / _wait): two batches in
+        # flight, each with its own page-locked result buffers; every step still moves its queries in and its rows out
+        # (the kernel reads / writes the page-locked buffers over PCIe itself).  The host consumes batch s-2 before it
+        # submits batch s.  B200HNSW_BENCH_SYNC_E2E=1 measures the blocking call instead.
+        outs = []
+        for _ in range(2):
+            l_ = torch.empty((a.nq, a.k), dtype=torch.int64).pin_memory()
+            d_ = torch.empty((a.nq, a.k), dtype=torch.float32).pin_memory()
+            c_ = torch.empty((a.nq,), dtype=torch.int32).pin_memory()
+            outs.append({"labels": l_.numpy().view(np.uint64), "dists": d_.numpy(), "counts": c_.numpy().view(np.uint32),
+                         "_keep": (l_, d_, c_)})
+        hq_np = [h.numpy() for h in hq]
+
+        def e2e_loop(steps):
+            tickets = [None, None]
+            for s in range(steps):
+                j = s % 2
+                if tickets[j] is not None:
+                    idx.searchKnnBatchWait(tickets[j])
+                tickets[j] = idx.searchKnnBatchSubmit(hq_np[s % len(hq_np)], a.k, outs[j], ef=ef)
+            for t in tickets:
+                if t is not None:
+                    idx.searchKnnBatchWait(t)
     else:
         def e2e_loop(steps):
             for s in range(steps):
@@ -770,7 +794,8 @@ def run_b200(a, rank, local_rank, world):
             "e2e": {"value": world * a.nq * a.steps / e2e_s,
                     "unit": "queries/s" if (world == 1 or replica) else "shard-searches/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
-                    "api": "b200hnsw_search_batch (host pointers, pinned)" if sw == 1 else
+                    "api": ("b200hnsw_search_batch (host pointers, pinned, blocking call)" if os.environ.get("B200HNSW_BENCH_SYNC_E2E")
+                            else "b200hnsw_search_batch_submit / _wait (host pointers, pinned; two batches in flight)") if sw == 1 else
                            "PipelinedShardSearch.submit_host: pinned H2D, b200hnsw_search_batch_device, packed NCCL "
                            "all_gather, merge kernel, pinned D2H; two batches in flight" if pipe is not None else
                            "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},

@@ -127,6 +127,15 @@ int b200hnsw_flush(b200hnsw_index *h);
  * elements are marked deleted or a filter is given at most 2^30 elements (one id bit carries the mark). */
 int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef, uint64_t *labels_out,
                           float *dists_out, uint32_t *counts_out, uint32_t *work_out);
+/* Asynchronous form for a serving loop that keeps more than one batch in flight: with PAGE-LOCKED Q / labels_out /
+ * dists_out / counts_out the launch is enqueued (the kernel reads the queries and stores the rows over PCIe itself) and
+ * the call returns a ticket at once; b200hnsw_search_batch_wait blocks until that batch is complete.  The buffers must
+ * stay valid and untouched until then.  At most four batches may be in flight per index (a fifth submit waits for a
+ * free context); pageable buffers make submit complete the search synchronously and return ticket 0 (wait(0) is a no-op).
+ * Calls that change the index wait for the launches in flight. */
+int b200hnsw_search_batch_submit(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef, uint64_t *labels_out,
+                                 float *dists_out, uint32_t *counts_out, uint64_t *ticket_out);
+int b200hnsw_search_batch_wait(b200hnsw_index *h, uint64_t ticket);
 /* Same, with DEVICE pointers on the index's device, enqueued on cuda_stream (a cudaStream_t; NULL = legacy
  * default stream) without host synchronisation. */
 int b200hnsw_search_batch_device(b200hnsw_index *h, const float *dQ, size_t nq, size_t k, size_t ef,

@@ -50,7 +50,7 @@ class _Stats(C.Structure):
 EXPORTS = [
     "b200hnsw_last_error", "b200hnsw_abi_version", "b200hnsw_device_count", "b200hnsw_create", "b200hnsw_load",
     "b200hnsw_save", "b200hnsw_destroy", "b200hnsw_set_ef", "b200hnsw_add_batch", "b200hnsw_add_batch_replace_deleted", "b200hnsw_flush",
-    "b200hnsw_search_batch", "b200hnsw_search_batch_filtered", "b200hnsw_get_labels", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
+    "b200hnsw_search_batch", "b200hnsw_search_batch_submit", "b200hnsw_search_batch_wait", "b200hnsw_search_batch_filtered", "b200hnsw_get_labels", "b200hnsw_search_batch_device", "b200hnsw_get_info", "b200hnsw_get_levels",
     "b200hnsw_get_linklist", "b200hnsw_get_label", "b200hnsw_get_data", "b200hnsw_get_data_by_label",
     "b200hnsw_mark_delete", "b200hnsw_unmark_delete", "b200hnsw_resize", "b200hnsw_index_file_size",
     "b200hnsw_get_stats", "b200hnsw_sharded_create", "b200hnsw_sharded_load", "b200hnsw_sharded_save",
@@ -99,6 +99,8 @@ def load_library():
     L.b200hnsw_add_batch_replace_deleted.argtypes = [vp, vp, vp, sz]
     L.b200hnsw_flush.argtypes = [vp]
     L.b200hnsw_search_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp]
+    L.b200hnsw_search_batch_submit.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, C.POINTER(C.c_uint64)]
+    L.b200hnsw_search_batch_wait.argtypes = [vp, C.c_uint64]
     L.b200hnsw_search_batch_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp, vp]
     L.b200hnsw_search_batch_filtered.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp, vp]
     L.b200hnsw_get_labels.argtypes = [vp, vp, sz]
@@ -290,6 +292,21 @@ class HierarchicalNSW:
         if work:
             out.update(D=w[:, 0].copy(), H0=w[:, 1].copy(), Hup=w[:, 2].copy(), resets=w[:, 3].copy())
         return out
+
+    def searchKnnBatchSubmit(self, Q, k, out, ef=0):
+        """Asynchronous searchKnnBatch (b200hnsw_search_batch_submit): `Q` and out["labels"/"dists"/"counts"] must be
+        page-locked numpy views that stay alive and untouched until searchKnnBatchWait(ticket) returns."""
+        assert Q.dtype == np.float32 and Q.flags.c_contiguous and Q.shape[1] == self.space.dim
+        nq = Q.shape[0]
+        labels, dists, counts = out["labels"], out["dists"], out["counts"]
+        assert labels.shape == (nq, k) and labels.dtype == np.uint64 and dists.shape == (nq, k) and dists.dtype == np.float32
+        t = C.c_uint64()
+        _chk(self._L.b200hnsw_search_batch_submit(self._h, _ptr(Q), nq, k, ef, _ptr(labels), _ptr(dists), _ptr(counts),
+                                                  C.byref(t)))
+        return t.value
+
+    def searchKnnBatchWait(self, ticket):
+        _chk(self._L.b200hnsw_search_batch_wait(self._h, ticket))
 
     def searchKnnFiltered(self, Q, k, is_id_allowed, ef=0):
         """searchKnn(query, k, isIdAllowed) batched: `is_id_allowed(label) -> bool` plays BaseFilterFunctor

@@ -373,9 +373,10 @@ int BruteIndex::search_device(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const bool want_tensor = force && !strcmp(force, "tensor");
     const bool want_stream = force && !strcmp(force, "stream");
     const size_t n = host.cur;
-    // measured on 1M x 768 (scripts/bench_bruteforce.py): streaming wins up to 8 queries, the tensor path (one 256-query
-    // tile, ~1.4 ms) from there on; on small indexes its fixed cost (a dozen launches) is not worth it
-    const bool tensor_pays = (double)n * (double)nq >= 6.7e7 || (nq > 8 && n >= 131072);
+    // measured on 1M x 768 (scripts/probe_bf_small.py, round 2): the tensor path reads the bf16 copy of the rows (half the
+    // bytes of the fp32 rows the streaming scan walks) and wins at EVERY batch size on a large index -- 0.47 ms against
+    // 0.76 ms for one query, 0.49 against 1.47 ms for eight; on small indexes its fixed cost (a dozen launches) does not pay
+    const bool tensor_pays = (double)n * (double)nq >= 6.7e7 || n >= 131072;
     if (!want_scan && !want_stream && k <= (cur_mask ? cur_mask_rows : n) && (want_tensor || tensor_pays)) {
         const int rc = search_tensor(dQ_, nq, k, dl, dd, dc, st);
         if (rc <= 0) { last_path = 1; return rc; }  // done, or a real error; rc == 1 -> fall through to the scan

@@ -52,6 +52,7 @@ static size_t env_size(const char *name, size_t dflt) {
 // addPoint staging (hnswalg.h:1153-1211,1255-1265): everything that does not need a distance.
 int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted) {
     std::unique_lock<std::shared_mutex> g(rw);
+    drain_async();
     struct StagedFlag {  // whatever path leaves this function, has_staged reflects the host image
         HnswIndex &ix;
         ~StagedFlag() { ix.has_staged = ix.linked < ix.host.cur; }
@@ -366,6 +367,7 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
 int HnswIndex::flush() {
     if (!has_staged) return 0;  // the common case of a search: nothing staged, no exclusive lock
     std::unique_lock<std::shared_mutex> g(rw);
+    drain_async();
     return flush_locked();
 }
 

@@ -106,6 +106,7 @@ int b200hnsw_save(b200hnsw_index *h, const char *path) {
     B200_GUARD_BEGIN
     if (!h || !path) { set_error("null argument"); return B200HNSW_E_ARG; }
     std::unique_lock<std::shared_mutex> lk(h->ix.rw);
+    h->ix.drain_async();
     int rc = h->ix.flush_locked();
     if (!rc) rc = h->ix.sync_host_mirror();
     if (rc) return rc;
@@ -154,6 +155,21 @@ int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k
     if (nq == 1 && Q && labels_out && dists_out && k)  // one query per call: coalesce concurrent callers into one launch
         return h->ix.search_coalesced(Q, k, ef, labels_out, dists_out, counts_out, work_out);
     return h->ix.search_host(Q, nq, k, ef, labels_out, dists_out, counts_out, work_out);
+    B200_GUARD_END
+}
+
+int b200hnsw_search_batch_submit(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef, uint64_t *labels_out,
+                                 float *dists_out, uint32_t *counts_out, uint64_t *ticket_out) {
+    B200_GUARD_BEGIN
+    if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    return h->ix.search_submit(Q, nq, k, ef, labels_out, dists_out, counts_out, ticket_out);
+    B200_GUARD_END
+}
+
+int b200hnsw_search_batch_wait(b200hnsw_index *h, uint64_t ticket) {
+    B200_GUARD_BEGIN
+    if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
+    return h->ix.search_wait(ticket);
     B200_GUARD_END
 }
 
@@ -210,6 +226,7 @@ int b200hnsw_get_linklist(b200hnsw_index *h, uint32_t id, int level, const uint3
     int rc = 0;
     if (h->ix.has_staged || h->ix.mirror_dirty) {  // refresh the host mirror; otherwise a shared lock is enough
         std::unique_lock<std::shared_mutex> xl(h->ix.rw);
+        h->ix.drain_async();
         rc = h->ix.flush_locked();
         if (!rc) rc = h->ix.sync_host_mirror();
         if (rc) return rc;
@@ -254,6 +271,7 @@ int b200hnsw_mark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:853-
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
     std::unique_lock<std::shared_mutex> lk(h->ix.rw);
+    h->ix.drain_async();
     b200::HostImage &m = h->ix.host;
     auto it = m.label_lookup.find(label);
     if (it == m.label_lookup.end()) { set_error("Label not found"); return B200HNSW_E_LABEL; }
@@ -270,6 +288,7 @@ int b200hnsw_unmark_delete(b200hnsw_index *h, uint64_t label) {  // hnswalg.h:89
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
     std::unique_lock<std::shared_mutex> lk(h->ix.rw);
+    h->ix.drain_async();
     b200::HostImage &m = h->ix.host;
     auto it = m.label_lookup.find(label);
     if (it == m.label_lookup.end()) { set_error("Label not found"); return B200HNSW_E_LABEL; }
@@ -286,6 +305,7 @@ int b200hnsw_resize(b200hnsw_index *h, size_t new_max) {  // hnswalg.h:633-656
     B200_GUARD_BEGIN
     if (!h) { set_error("null handle"); return B200HNSW_E_ARG; }
     std::unique_lock<std::shared_mutex> lk(h->ix.rw);
+    h->ix.drain_async();
     if (new_max < h->ix.host.cur) {
         set_error("Cannot resize, max element is less than the current number of elements");
         return B200HNSW_E_ARG;

@@ -454,6 +454,7 @@ struct SearchLock {
             sh.unlock();
         }
         ex = std::unique_lock<std::shared_mutex>(ix.rw);
+        ix.drain_async();  // the marks on the device are about to change under launches still in flight
     }
 };
 
@@ -481,6 +482,81 @@ int HnswIndex::search_host(const float *Q, size_t nq, size_t k, size_t ef_, uint
     }
     release_ctx(c);
     return rc;
+}
+
+void HnswIndex::drain_async() {
+    std::vector<cudaStream_t> pending;
+    {
+        std::lock_guard<std::mutex> lk(ctx_mu);
+        for (auto &c : ctxs)
+            if (c->async_pending && c->stream) pending.push_back(c->stream);
+    }
+    for (cudaStream_t st : pending) cudaStreamSynchronize(st);
+}
+
+int HnswIndex::search_submit(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists,
+                             uint32_t *counts, uint64_t *ticket_out) {
+    if (!ticket_out) { set_error("ticket_out is null"); return B200HNSW_E_ARG; }
+    *ticket_out = 0;
+    if (nq == 0) return 0;
+    if (!Q || !labels || !dists || k == 0) {
+        set_error("search: null pointer or k == 0");
+        return B200HNSW_E_ARG;
+    }
+    int rc = flush();
+    if (rc) return rc;
+    B200_CUDA_OK(cudaSetDevice(dev.device));
+    void *dq = nullptr, *dl = nullptr, *dd = nullptr, *dc = nullptr;
+    bool ok = cudaHostGetDevicePointer(&dq, (void *)Q, 0) == cudaSuccess &&
+              cudaHostGetDevicePointer(&dl, (void *)labels, 0) == cudaSuccess &&
+              cudaHostGetDevicePointer(&dd, (void *)dists, 0) == cudaSuccess;
+    if (ok && counts) ok = cudaHostGetDevicePointer(&dc, (void *)counts, 0) == cudaSuccess;
+    if (!ok) {  // pageable buffers: nothing to overlap with, the call completes here and the ticket is 0
+        cudaGetLastError();
+        return search_host(Q, nq, k, ef_, labels, dists, counts, nullptr);
+    }
+    SearchCtx *c = acquire_ctx();
+    rc = c->ensure(1, 1, host.dim);  // stream + events only
+    if (!rc) {
+        SearchLock lock(*this, false);
+        rc = launch_search((const float *)dq, nq, k, ef_, (uint64_t *)dl, (float *)dd, (uint32_t *)dc, nullptr, c->stream);
+        if (!rc) {
+            std::lock_guard<std::mutex> lk(ctx_mu);
+            c->async_pending = true;
+        }
+    }
+    if (rc) {
+        release_ctx(c);
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(ctx_mu);
+    for (size_t i = 0; i < ctxs.size(); i++)
+        if (ctxs[i].get() == c) *ticket_out = i + 1;
+    return 0;
+}
+
+int HnswIndex::search_wait(uint64_t ticket) {
+    if (ticket == 0) return 0;
+    SearchCtx *c = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx_mu);
+        if (ticket > ctxs.size() || !ctxs[ticket - 1]->async_pending) {
+            set_error("search_wait: no launch is pending for this ticket");
+            return B200HNSW_E_ARG;
+        }
+        c = ctxs[ticket - 1].get();
+    }
+    const cudaError_t e = cudaStreamSynchronize(c->stream);
+    {
+        std::lock_guard<std::mutex> lk(ctx_mu);
+        c->async_pending = false;
+    }
+    release_ctx(c);
+    if (e != cudaSuccess) {
+        set_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+        return B200HNSW_E_CUDA;
+    }
+    return 0;
 }
 
 int HnswIndex::search_host_locked(SearchCtx &c, const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels,

@@ -44,6 +44,7 @@ struct SearchCtx {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     bool busy = false;
+    bool async_pending = false;  // a search_submit launch has not been waited for yet
     ~SearchCtx();
     int ensure(size_t nq, size_t k, size_t dim);
 };
@@ -74,6 +75,12 @@ struct HnswIndex {
     std::vector<std::unique_ptr<SearchCtx>> ctxs;
     SearchCtx *acquire_ctx();
     void release_ctx(SearchCtx *c);
+    // asynchronous form of search_host for page-locked buffers: submit enqueues the zero-copy launch on a context of
+    // its own and returns a ticket, wait blocks until that launch has finished.  Writers drain pending launches first.
+    int search_submit(const float *Q, size_t nq, size_t k, size_t ef_, uint64_t *labels, float *dists, uint32_t *counts,
+                      uint64_t *ticket_out);
+    int search_wait(uint64_t ticket);
+    void drain_async();  // caller holds `rw` exclusively
 
     // micro-batching of concurrent single-query calls
     struct Pending {

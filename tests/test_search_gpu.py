@@ -347,3 +347,37 @@ def test_concurrent_callers_share_the_index(lib, graphs):
     assert not errors, errors[:3]
     after = gpu.searchKnnBatch(Q, 10, ef=64)
     assert np.array_equal(after["labels"], quiet["labels"]) and np.array_equal(after["dists"], quiet["dists"])
+
+
+def test_submit_wait_equals_blocking_call(lib, graphs):
+    """b200hnsw_search_batch_submit / _wait with page-locked buffers (the kernel reads the queries and stores the rows over
+    PCIe itself): several batches in flight return exactly what the blocking call returns; a writer in between waits for
+    them; pageable buffers complete synchronously with ticket 0."""
+    import torch
+    gspec = graphs["lowrank_d128"]
+    gpu = lib.HierarchicalNSW(lib.L2Space(gspec["d"]), gspec["path"])
+    Q = np.ascontiguousarray(np.tile(gspec["Q"], (3, 1)))
+    want = gpu.searchKnnBatch(Q, 10, ef=40)
+    qp = torch.from_numpy(Q).pin_memory()
+    outs, tickets = [], []
+    for i in range(3):
+        l_ = torch.empty((len(Q), 10), dtype=torch.int64).pin_memory()
+        d_ = torch.empty((len(Q), 10), dtype=torch.float32).pin_memory()
+        c_ = torch.zeros((len(Q),), dtype=torch.int32).pin_memory()
+        outs.append((l_, d_, c_))
+        tickets.append(gpu.searchKnnBatchSubmit(qp.numpy(), 10, {"labels": l_.numpy().view(np.uint64), "dists": d_.numpy(),
+                                                                 "counts": c_.numpy().view(np.uint32)}, ef=40))
+    assert all(t > 0 for t in tickets) and len(set(tickets)) == 3
+    gpu.markDelete(7)          # a writer: drains the launches in flight first
+    gpu.unmarkDelete(7)
+    for t in tickets:
+        gpu.searchKnnBatchWait(t)
+    for l_, d_, c_ in outs:
+        assert np.array_equal(l_.numpy().view(np.uint64), want["labels"]) and np.array_equal(d_.numpy(), want["dists"])
+        assert (c_.numpy() == 10).all()
+    with pytest.raises(lib.B200Error):
+        gpu.searchKnnBatchWait(tickets[0])                       # already waited for
+    out = {"labels": np.empty((len(Q), 10), np.uint64), "dists": np.empty((len(Q), 10), np.float32),
+           "counts": np.zeros(len(Q), np.uint32)}
+    assert gpu.searchKnnBatchSubmit(Q, 10, out, ef=40) == 0      # pageable: done synchronously
+    assert np.array_equal(out["labels"], want["labels"])
