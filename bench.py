@@ -693,6 +693,16 @@ def run_b200(a, rank, local_rank, world):
     t0 = time.perf_counter()
     e2e_loop(a.steps)
     e2e_s = time.perf_counter() - t0
+    e2e_blocking = None
+    if sw == 1:  # the blocking form of the same call, for the record: one batch at a time, nothing overlaps its tail
+        for s in range(3):
+            e2e_step(s)
+        t0b = time.perf_counter()
+        for s in range(a.steps):
+            e2e_step(s)
+        tb = time.perf_counter() - t0b
+        e2e_blocking = {"value": a.nq * a.steps / tb, "unit": "queries/s", "ms_per_step": 1e3 * tb / a.steps,
+                        "api": "b200hnsw_search_batch (host pointers, pinned, blocking call)"}
     if dist:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -793,7 +803,7 @@ def run_b200(a, rank, local_rank, world):
             "clocks": clocks, "per_rank": rank_diag,
             "e2e": {"value": world * a.nq * a.steps / e2e_s,
                     "unit": "queries/s" if (world == 1 or replica) else "shard-searches/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps, "blocking_call": e2e_blocking,
                     "api": ("b200hnsw_search_batch (host pointers, pinned, blocking call)" if os.environ.get("B200HNSW_BENCH_SYNC_E2E")
                             else "b200hnsw_search_batch_submit / _wait (host pointers, pinned; two batches in flight)") if sw == 1 else
                            "PipelinedShardSearch.submit_host: pinned H2D, b200hnsw_search_batch_device, packed NCCL "

@@ -383,6 +383,8 @@ int HnswIndex::flush_locked() {
     const size_t rec = m.size_data;
     const size_t build_ratio = env_size("B200HNSW_BUILD_RATIO", 32);
     const size_t max_batch = env_size("B200HNSW_BUILD_BATCH", 16384);
+    const size_t ramp_ratio = env_size("B200HNSW_BUILD_RAMP_RATIO", build_ratio);
+    const size_t ramp_until = env_size("B200HNSW_BUILD_RAMP_UNTIL", 65536);
 
     // ---- upload vectors + labels of the staged points (records carry empty lists) ----
     {
@@ -465,7 +467,9 @@ int HnswIndex::flush_locked() {
             lk = 1;
         }
         while (lk < m.cur) {
-            size_t B = std::max<size_t>(1, std::min(max_batch, lk / build_ratio));
+            // while fewer points are linked than a batch needs to fill the GPU, a batch may be a larger fraction of them
+            const size_t ratio = lk < ramp_until ? ramp_ratio : build_ratio;
+            size_t B = std::max<size_t>(1, std::min(max_batch, lk / ratio));
             B = std::min(B, m.cur - lk);
             BatchPlan bp{(uint32_t)lk, 0, (uint32_t)lp_all.size(), 0, ent, ml};
             size_t used = 0, nl = 0;

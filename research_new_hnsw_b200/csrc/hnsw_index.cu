@@ -261,7 +261,10 @@ int HnswIndex::upload_flags(const uint8_t *allowed, const uint32_t *extra, size_
 // never rebuilds it (D ~ 30*ef + 500 on the 1M x 128, M=32 graph).  Smaller teams trade table
 // size for resident queries: the table is rebuilt from the buffer at 5/8 load (re-evaluations only).
 uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
-    const size_t need = 2 * (ef + list_cap);
+    // The table is rebuilt from the buffer when it is more than 5/8 full at the START of a hop, and a hop inserts up to
+    // list_cap ids: 5/8 * size + list_cap must stay below the size (or hash_insert's probe loop would never find a free
+    // slot), and the rebuilt table (<= ef entries) must itself be below the mark.
+    const size_t need = std::max(2 * (ef + list_cap), 8 * list_cap / 3 + 64);
     if (const char *e = getenv("B200HNSW_HASH_BITS")) {
         const int b = atoi(e);
         if (b >= 8 && b <= 15) {

@@ -79,6 +79,7 @@ struct HostImage {
         upper.assign(max_elements, {});
         levels.assign(max_elements, 0);
         label_lookup.clear();
+        label_lookup.reserve(max_elements);  // addPoint of a million labels: no rehashing on the way
         return true;
     }
 

@@ -35,4 +35,7 @@ if which == "small":
 else:
     n = int(which)
     X = bind.lowrank_data(n, 128, seed=1); Q = bind.lowrank_data(2000, 128, seed=2)
-    run("c2-lowrank", 0, X, Q, 32, 200, [8, 16, 32], [16, 32, 64])
+    for ramp in os.environ.get("PROBE_RAMPS", "32").split(","):
+        os.environ["B200HNSW_BUILD_RAMP_RATIO"] = ramp
+        print("== ramp ratio", ramp, flush=True)
+        run("c2-lowrank", 0, X, Q, 32, 200, [int(r) for r in os.environ.get("PROBE_RATIOS", "32").split(",")], [16, 28, 32, 64])
