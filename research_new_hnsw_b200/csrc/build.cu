@@ -383,7 +383,9 @@ int HnswIndex::flush_locked() {
     const size_t rec = m.size_data;
     const size_t build_ratio = env_size("B200HNSW_BUILD_RATIO", 32);
     const size_t max_batch = env_size("B200HNSW_BUILD_BATCH", 16384);
-    const size_t ramp_ratio = env_size("B200HNSW_BUILD_RAMP_RATIO", build_ratio);
+    // measured at C5 (gpurun_out/r02_build_ramp.log): ramp ratio 32 / 16 / 8 / 4 -> 1185 / 780 / 555 / 432 launches,
+    // 1634 / 1540 / 1502 / 1480 ms of kernels, recall@10 at ef=28 0.9486 / 0.9485 / 0.9486 / 0.9507 (reference-built: 0.950)
+    const size_t ramp_ratio = env_size("B200HNSW_BUILD_RAMP_RATIO", std::min<size_t>(build_ratio, 8));
     const size_t ramp_until = env_size("B200HNSW_BUILD_RAMP_UNTIL", 65536);
 
     // ---- upload vectors + labels of the staged points (records carry empty lists) ----
@@ -468,7 +470,8 @@ int HnswIndex::flush_locked() {
         }
         while (lk < m.cur) {
             // while fewer points are linked than a batch needs to fill the GPU, a batch may be a larger fraction of them
-            const size_t ratio = lk < ramp_until ? ramp_ratio : build_ratio;
+            // (only on builds that go far beyond the ramp: a small index is built at the validated ratio throughout)
+            const size_t ratio = (lk < ramp_until && m.cur >= 4 * ramp_until) ? ramp_ratio : build_ratio;
             size_t B = std::max<size_t>(1, std::min(max_batch, lk / ratio));
             B = std::min(B, m.cur - lk);
             BatchPlan bp{(uint32_t)lk, 0, (uint32_t)lp_all.size(), 0, ent, ml};
