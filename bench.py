@@ -532,9 +532,31 @@ def run_b200(a, rank, local_rank, world):
         torch.cuda.synchronize()
         works.append(w.cpu().numpy().astype(np.int64))
     from research_new_hnsw_b200.sharded import PipelinedShardSearch
-    pipe = None
+    pipe, exchange = None, None
     if sw > 1 and not os.environ.get("B200HNSW_BENCH_NO_PIPELINE"):
-        pipe = PipelinedShardSearch(idx, a.nq, a.k, dev, depth=int(os.environ.get("B200HNSW_PIPE_DEPTH", "2")))
+        # exchange of the per-shard rows: peer-to-peer pushes by the copy engines + stream memory flags (csrc/exchange.cu);
+        # B200HNSW_EXCHANGE=nccl (or a failed IPC set-up on any rank) -> one packed NCCL all_gather per batch
+        exchange = os.environ.get("B200HNSW_EXCHANGE", "p2p")
+        depth = int(os.environ.get("B200HNSW_PIPE_DEPTH", "2"))
+        if exchange == "p2p":
+            ok = torch.ones(1, device=dev)
+            try:
+                pipe = PipelinedShardSearch(idx, a.nq, a.k, dev, depth=depth, exchange="p2p")
+            except Exception as e:  # noqa: BLE001 -- no peer access / IPC on this box
+                sys.stderr.write("rank %d: p2p exchange unavailable (%s)\n" % (rank, e))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                pipe, exchange = None, "nccl"
+        if pipe is None:
+            pipe = PipelinedShardSearch(idx, a.nq, a.k, dev, depth=depth)
+        # the pipelined exchange that is timed below must return the rows the inline check above has just verified
+        pl_, pd_, pev = pipe.submit(dbatches[0].data_ptr(), ef)
+        pev.synchronize()
+        if not (np.array_equal(pl_.cpu().numpy().view(np.uint64), ml) and np.array_equal(pd_.cpu().numpy(), md)):
+            raise AssertionError("pipelined %s exchange returned different rows" % exchange)
+        merge_check["timed_exchange"] = exchange
+        merge_check["timed_exchange_equal_to_checked_rows"] = True
     for s in range(a.warmup):
         if pipe is not None:
             pipe.submit(dbatches[s % len(dbatches)].data_ptr(), ef)
@@ -687,6 +709,12 @@ def run_b200(a, rank, local_rank, world):
             for s in range(steps):
                 e2e_step(s)
 
+    if pipe is not None:  # the host-facing path returns the rows that were verified above
+        ev_ = pipe.submit_host(hq[0], ef, hl2[0], hd2[0])
+        ev_.synchronize()
+        if not (np.array_equal(hl2[0].numpy().view(np.uint64), ml) and np.array_equal(hd2[0].numpy(), md)):
+            raise AssertionError("submit_host returned different rows")
+        merge_check["host_path_equal_to_checked_rows"] = True
     e2e_loop(3)
     if dist:
         dist.barrier()
@@ -789,12 +817,13 @@ def run_b200(a, rank, local_rank, world):
                        "parallelism": "1 GPU" if world == 1 else
                        ("replica%d: the same %d-point index on every GPU, each GPU serves its own query batches, no "
                         "data-path collective" % (world, a.n)) if replica else
-                       "shard%d: one %d-point sub-index per GPU (%d points in total), queries replicated, ONE packed NCCL "
-                       "all_gather + GPU merge per batch%s; value counts (query, shard) searches, merged_qps = value/%d is the "
+                       "shard%d: one %d-point sub-index per GPU (%d points in total), queries replicated, per-shard rows exchanged by %s + GPU merge per batch%s; value counts (query, shard) searches, merged_qps = value/%d is the "
                        "rate of merged answers over the whole data set; ef is the smallest whose MERGED recall reaches the "
                        "target, so it falls as N grows (each shard owes only its share of the global top-k)"
-                       % (world, a.n, world * a.n, ", exchange of batch i overlapped with the search of batch i+1" if pipe else "",
-                          world),
+                       % (world, a.n, world * a.n,
+                          "peer-to-peer copy-engine pushes over NVLink with stream memory flags (no collective kernel)" if exchange == "p2p"
+                          else "ONE packed NCCL all_gather",
+                          ", exchange of batch i overlapped with the search of batch i+1" if pipe else "", world),
                        "ground_truth": gt_check, "merge_check": merge_check,
                        "l2_policy": "inputs larger than L2 (index %.0f MB vs 126 MB L2); %d distinct query batches cycled"
                                     % ((a.n * (a.dim * 4 + 8 * a.M)) / 1e6, len(batches)),
@@ -806,8 +835,9 @@ def run_b200(a, rank, local_rank, world):
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / a.steps, "blocking_call": e2e_blocking,
                     "api": ("b200hnsw_search_batch (host pointers, pinned, blocking call)" if os.environ.get("B200HNSW_BENCH_SYNC_E2E")
                             else "b200hnsw_search_batch_submit / _wait (host pointers, pinned; two batches in flight)") if sw == 1 else
-                           "PipelinedShardSearch.submit_host: pinned H2D, b200hnsw_search_batch_device, packed NCCL "
-                           "all_gather, merge kernel, pinned D2H; two batches in flight" if pipe is not None else
+                           ("PipelinedShardSearch.submit_host: page-locked queries read and merged rows stored by the kernels "
+                            "themselves (zero-copy), b200hnsw_search_batch_device, %s, merge kernel; two batches in flight" % ("b200hnsw_exchange_step (P2P pushes)" if exchange == "p2p"
+                                                                     else "packed NCCL all_gather")) if pipe is not None else
                            "ShardedSearcher: pinned H2D, b200hnsw_search_batch_device, NCCL all_gather, merge kernel, D2H"},
             "gpu_launches": a.steps * (1 if sw == 1 else 2),  # search kernel (+ merge kernel at N > 1)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -130,8 +130,8 @@ int b200hnsw_search_batch(b200hnsw_index *h, const float *Q, size_t nq, size_t k
 /* Asynchronous form for a serving loop that keeps more than one batch in flight: with PAGE-LOCKED Q / labels_out /
  * dists_out / counts_out the launch is enqueued (the kernel reads the queries and stores the rows over PCIe itself) and
  * the call returns a ticket at once; b200hnsw_search_batch_wait blocks until that batch is complete.  The buffers must
- * stay valid and untouched until then.  At most four batches may be in flight per index (a fifth submit waits for a
- * free context); pageable buffers make submit complete the search synchronously and return ticket 0 (wait(0) is a no-op).
+ * stay valid and untouched until then.  At most four batches may be in flight per index (one more submit fails with
+ * B200HNSW_E_STATE); pageable buffers make submit complete the search synchronously and return ticket 0 (wait(0) is a no-op).
  * Calls that change the index wait for the launches in flight. */
 int b200hnsw_search_batch_submit(b200hnsw_index *h, const float *Q, size_t nq, size_t k, size_t ef, uint64_t *labels_out,
                                  float *dists_out, uint32_t *counts_out, uint64_t *ticket_out);
@@ -208,6 +208,23 @@ int b200hnsw_sharded_search_batch(b200hnsw_sharded *h, const float *Q, size_t nq
                                   uint64_t *labels_out, float *dists_out, uint32_t *counts_out);
 /* CUDA-event time of the last sharded search (H2D of the queries on every device .. merge kernel), milliseconds. */
 int b200hnsw_sharded_last_ms(b200hnsw_sharded *h, double *ms_out);
+
+/* ---- result exchange between processes, one per GPU, without a collective kernel ----------------
+ * Every rank owns a receive area in its HBM, published as a B200HNSW_EXCHANGE_DESC_BYTES descriptor (CUDA IPC handles)
+ * that the host gathers from all ranks by whatever means it has (the Python form uses torch.distributed once at
+ * set-up).  Per step s = 1, 2, ...: the rank's search writes its packed block ([nq*k labels | nq*k dists], as for
+ * b200hnsw_merge_topk_packed_device) into *my_block_out of b200hnsw_exchange_slot(s); b200hnsw_exchange_step(s, stream)
+ * then pushes it into every peer's area with copy-engine copies over NVLink, raises the peers' flags with stream memory
+ * writes and makes `stream` wait (stream memory waits, no SM) until the blocks of all peers for step s have landed in
+ * *all_blocks_out, which the merge kernel reads in place.  Three areas are cycled, so a rank may run one step ahead. */
+#define B200HNSW_EXCHANGE_DESC_BYTES 128
+typedef struct b200hnsw_exchange b200hnsw_exchange;
+int b200hnsw_exchange_create(int device, size_t world, size_t rank, size_t block_bytes, b200hnsw_exchange **out,
+                             void *desc_out /* B200HNSW_EXCHANGE_DESC_BYTES */);
+int b200hnsw_exchange_connect(b200hnsw_exchange *x, const void *all_descs /* world descriptors, rank order */);
+int b200hnsw_exchange_slot(b200hnsw_exchange *x, uint32_t step, void **my_block_out, void **all_blocks_out);
+int b200hnsw_exchange_step(b200hnsw_exchange *x, uint32_t step, void *cuda_stream);
+void b200hnsw_exchange_destroy(b200hnsw_exchange *x);
 
 /* ---- BruteforceSearch<float> (bruteforce.h) -------------------------------------------------------------- */
 /* BruteforceSearch(space, maxElements), bruteforce.h:48-59 */

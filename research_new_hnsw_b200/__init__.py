@@ -12,6 +12,7 @@ from .capi import (  # noqa: F401
     HierarchicalNSW,
     InnerProductSpace,
     L2Space,
+    P2PExchange,
     ShardedHierarchicalNSW,
     build_library,
     device_count,
@@ -22,6 +23,6 @@ from .capi import (  # noqa: F401
 )
 
 __all__ = [
-    "B200Error", "BruteforceSearch", "HierarchicalNSW", "InnerProductSpace", "L2Space", "ShardedHierarchicalNSW", "build_library",
+    "B200Error", "BruteforceSearch", "HierarchicalNSW", "InnerProductSpace", "L2Space", "P2PExchange", "ShardedHierarchicalNSW", "build_library",
     "device_count", "lib_path", "load_library", "merge_topk_device", "merge_topk_packed_device",
 ]

@@ -56,7 +56,8 @@ EXPORTS = [
     "b200hnsw_get_stats", "b200hnsw_sharded_create", "b200hnsw_sharded_load", "b200hnsw_sharded_save",
     "b200hnsw_sharded_destroy", "b200hnsw_sharded_num_shards", "b200hnsw_sharded_get_shard", "b200hnsw_sharded_count",
     "b200hnsw_sharded_add_batch", "b200hnsw_sharded_flush", "b200hnsw_sharded_search_batch", "b200hnsw_sharded_last_ms",
-    "b200hnsw_merge_topk_device", "b200hnsw_merge_topk_packed_device", "b200bf_create", "b200bf_load", "b200bf_save",
+    "b200hnsw_exchange_create", "b200hnsw_exchange_connect", "b200hnsw_exchange_slot", "b200hnsw_exchange_step",
+    "b200hnsw_exchange_destroy", "b200hnsw_merge_topk_device", "b200hnsw_merge_topk_packed_device", "b200bf_create", "b200bf_load", "b200bf_save",
     "b200bf_destroy", "b200bf_add_batch", "b200bf_remove", "b200bf_search_batch", "b200bf_search_batch_device",
     "b200bf_search_batch_filtered", "b200bf_get_labels", "b200bf_count", "b200bf_get_stats",
 ]
@@ -127,6 +128,12 @@ def load_library():
     L.b200hnsw_sharded_flush.argtypes = [vp]
     L.b200hnsw_sharded_search_batch.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     L.b200hnsw_sharded_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
+    L.b200hnsw_exchange_create.argtypes = [C.c_int, sz, sz, sz, C.POINTER(vp), vp]
+    L.b200hnsw_exchange_connect.argtypes = [vp, vp]
+    L.b200hnsw_exchange_slot.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
+    L.b200hnsw_exchange_step.argtypes = [vp, C.c_uint32, vp]
+    L.b200hnsw_exchange_destroy.argtypes = [vp]
+    L.b200hnsw_exchange_destroy.restype = None
     L.b200hnsw_merge_topk_device.argtypes = [vp, vp, sz, sz, sz, vp, vp, vp]
     L.b200hnsw_merge_topk_packed_device.argtypes = [vp, sz, sz, sz, sz, vp, vp, vp]
     L.b200bf_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
@@ -519,6 +526,38 @@ class BruteforceSearch:
         s = _Stats()
         _chk(self._L.b200bf_get_stats(self._h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in _Stats._fields_}
+
+
+EXCHANGE_DESC_BYTES = 128
+
+
+class P2PExchange:
+    """b200hnsw_exchange_*: result blocks pushed peer to peer by the copy engines, stream memory operations as flags
+    (csrc/exchange.cu).  `gather_descs(my_desc: bytes) -> bytes` must return the descriptors of all ranks in rank order."""
+
+    def __init__(self, device, world, rank, block_bytes, gather_descs):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        desc = C.create_string_buffer(EXCHANGE_DESC_BYTES)
+        _chk(self._L.b200hnsw_exchange_create(device, world, rank, block_bytes, C.byref(self._h), desc))
+        alld = gather_descs(desc.raw)
+        assert len(alld) == world * EXCHANGE_DESC_BYTES
+        buf = C.create_string_buffer(alld, len(alld))
+        _chk(self._L.b200hnsw_exchange_connect(self._h, buf))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200hnsw_exchange_destroy(self._h)
+            self._h = None
+
+    def slot(self, step):
+        """-> (address of this rank's block, address of the [world][block] area) for `step` (numbered from 1)"""
+        mine, allb = C.c_void_p(), C.c_void_p()
+        _chk(self._L.b200hnsw_exchange_slot(self._h, step, C.byref(mine), C.byref(allb)))
+        return mine.value, allb.value
+
+    def step(self, step, stream=0):
+        _chk(self._L.b200hnsw_exchange_step(self._h, step, stream or None))
 
 
 def merge_topk_device(d_labels_in, d_dists_in, shards, nq, k, d_labels_out, d_dists_out, stream=0):

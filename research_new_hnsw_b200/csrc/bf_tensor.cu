@@ -684,10 +684,12 @@ static void launch_rerank(unsigned grid, size_t smem, cudaStream_t st, const flo
                           const float *xn2, const float *qn2, const float *Q, uint32_t dim, uint32_t d4, uint32_t lane_chunks,
                           const uint2 *cand, const uint32_t *cand_cnt, uint32_t cap, uint32_t k, uint32_t n,
                           uint64_t *out_l, float *out_d, uint32_t *out_c, uint32_t *overflow) {
-    static bool cfg = false;
-    if (!cfg) {
+    static bool cfg[16] = {};  // function attributes are per device
+    int dv = 0;
+    cudaGetDevice(&dv);
+    if (dv >= 16 || !cfg[dv]) {
         cudaFuncSetAttribute(bf_rerank_kernel<METRIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cfg = true;
+        if (dv < 16) cfg[dv] = true;
     }
     bf_rerank_kernel<METRIC><<<grid, kRrThreads, smem, st>>>(X, labels, xn2, qn2, Q, dim, d4, lane_chunks, cand, cand_cnt, cap,
                                                             k, n, out_l, out_d, out_c, overflow);
@@ -843,10 +845,10 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     mark();
     const size_t kth_smem = sampled * kKthQ * 4;
     if (kth_smem <= 160 * 1024) {
-        static bool kcfg = false;
-        if (!kcfg) {
+        static bool kcfg[16] = {};
+        if (device >= 16 || !kcfg[device]) {
             B200_CUDA_OK(cudaFuncSetAttribute(bf_kth_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            kcfg = true;
+            if (device < 16) kcfg[device] = true;
         }
         bf_kth_smem_kernel<<<(unsigned)(nq_pad / kKthQ), 256, kth_smem, st>>>(tz.panelmin, (uint32_t)sampled, (uint32_t)nq_pad,
                                                                              (uint32_t)nq, (uint32_t)k, tz.thr);

@@ -26,7 +26,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
-#include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "build_kernels.cuh"
@@ -136,9 +136,9 @@ int HnswIndex::relink_points(std::vector<uint32_t> ids, const std::vector<uint32
     {   // call order, one entry per point (a label given twice: the host image already holds the last vector)
         std::vector<uint32_t> uniq;
         uniq.reserve(ids.size());
-        std::unordered_map<uint32_t, bool> seen;
+        std::unordered_set<uint32_t> seen;
         for (uint32_t id : ids)
-            if (seen.emplace(id, true).second) uniq.push_back(id);
+            if (seen.insert(id).second) uniq.push_back(id);
         ids.swap(uniq);
     }
     B200_CUDA_OK(cudaSetDevice(dev.device));

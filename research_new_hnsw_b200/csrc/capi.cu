@@ -206,7 +206,7 @@ int b200hnsw_get_info(b200hnsw_index *h, b200hnsw_info *o) {
     const b200::HostImage &m = h->ix.host;
     memset(o, 0, sizeof(*o));
     o->cur_element_count = m.cur; o->max_elements = m.max_elements; o->num_deleted = m.num_deleted;
-    o->dim = m.dim; o->M = m.M; o->maxM = m.maxM; o->maxM0 = m.maxM0; o->ef_construction = m.efc; o->ef = h->ix.ef;
+    o->dim = m.dim; o->M = m.M; o->maxM = m.maxM; o->maxM0 = m.maxM0; o->ef_construction = m.efc; o->ef = h->ix.ef.load();
     o->size_data_per_element = m.size_data; o->size_links_per_element = m.size_links;
     o->size_links_level0 = m.size_links0; o->offset_data = m.off_data; o->label_offset = m.off_label;
     o->mult = m.mult; o->maxlevel = m.maxlevel; o->enterpoint_node = m.enterpoint;

@@ -40,7 +40,7 @@ int SearchCtx::ensure(size_t nq, size_t k, size_t dim) {
 }
 
 // A free context, or a new one while the pool is below its size (B200HNSW_SEARCH_CTXS, default 4), else wait.
-SearchCtx *HnswIndex::acquire_ctx() {
+SearchCtx *HnswIndex::acquire_ctx(bool wait) {
     static const size_t max_ctx = [] {
         const char *e = getenv("B200HNSW_SEARCH_CTXS");
         const int v = e ? atoi(e) : 4;
@@ -55,6 +55,7 @@ SearchCtx *HnswIndex::acquire_ctx() {
             ctxs.back()->busy = true;
             return ctxs.back().get();
         }
+        if (!wait) return nullptr;
         ctx_cv.wait(lk);
     }
 }
@@ -68,6 +69,8 @@ void HnswIndex::release_ctx(SearchCtx *c) {
 }
 
 HnswIndex::~HnswIndex() {
+    for (auto &c : ctxs)  // a launch of search_submit that nobody waited for must not outlive the arrays it reads
+        if (c->stream) cudaStreamSynchronize(c->stream);
     if (dev.cap || dev.err_flag) {
         cudaSetDevice(dev.device);
         dev.release();
@@ -319,7 +322,7 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
         fill_pad_rows(dd, dc, dw, nq, k, st);  // dist = +inf, counts = 0
         return 0;
     }
-    size_t efx = ef_ ? ef_ : ef;
+    size_t efx = ef_ ? ef_ : ef.load();
     efx = std::max(efx, k);  // hnswalg.h:1309
     if (efx > 4096) {
         set_error("ef > 4096 is not supported");
@@ -518,7 +521,12 @@ int HnswIndex::search_submit(const float *Q, size_t nq, size_t k, size_t ef_, ui
         cudaGetLastError();
         return search_host(Q, nq, k, ef_, labels, dists, counts, nullptr);
     }
-    SearchCtx *c = acquire_ctx();
+    // never block here: the caller may be the very thread that has to wait for the batches in flight
+    SearchCtx *c = acquire_ctx(false);
+    if (!c) {
+        set_error("search_submit: too many batches in flight (wait for one of them first)");
+        return B200HNSW_E_STATE;
+    }
     rc = c->ensure(1, 1, host.dim);  // stream + events only
     if (!rc) {
         SearchLock lock(*this, false);

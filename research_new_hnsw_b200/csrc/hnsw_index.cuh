@@ -53,7 +53,7 @@ struct HnswIndex {
     b200hnsw_params prm{};
     HostImage host;
     DeviceIndex dev;
-    size_t ef = 10;  // hnswalg.h:115
+    std::atomic<size_t> ef{10};  // hnswalg.h:115 (setEf is an unsynchronised write in the reference; atomic here)
     // Locking (the reference: label-op / link-list locks for writers, lock-free const searchKnn, hnswalg.h:40-43,59):
     // every call that changes the host image, the device graph or the delete marks holds `rw` exclusively; searches and
     // read-only accessors hold it shared.  C-ABI entry points take the lock; the *_locked / launch_* members assume it.
@@ -73,7 +73,7 @@ struct HnswIndex {
     std::mutex ctx_mu;
     std::condition_variable ctx_cv;
     std::vector<std::unique_ptr<SearchCtx>> ctxs;
-    SearchCtx *acquire_ctx();
+    SearchCtx *acquire_ctx(bool wait = true);  // wait = false: nullptr when every context is busy
     void release_ctx(SearchCtx *c);
     // asynchronous form of search_host for page-locked buffers: submit enqueues the zero-copy launch on a context of
     // its own and returns a ticket, wait blocks until that launch has finished.  Writers drain pending launches first.

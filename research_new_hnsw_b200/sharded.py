@@ -105,16 +105,71 @@ class PackedShardExchange:
         base = self.mine.data_ptr()
         return base, base + self.nq * self.k * 8
 
-    def exchange_and_merge(self, stream):
+    def exchange_and_merge(self, stream, out_ptrs=None):
+        """out_ptrs = (labels, dists) device-accessible addresses for the merged rows (default: this object's tensors)"""
         from . import capi
         if self.world == 1:
             src = self.mine
         else:
             self.dist.all_gather_into_tensor(self.all, self.mine, group=self.group)
             src = self.all
-        capi.merge_topk_packed_device(src.data_ptr(), self.block, self.world, self.nq, self.k, self.out_l.data_ptr(),
-                                      self.out_d.data_ptr(), stream)
+        ol, od = out_ptrs if out_ptrs else (self.out_l.data_ptr(), self.out_d.data_ptr())
+        capi.merge_topk_packed_device(src.data_ptr(), self.block, self.world, self.nq, self.k, ol, od, stream)
         return self.out_l, self.out_d
+
+
+class P2PShardExchange:
+    """Same role as PackedShardExchange without a collective: the rank's block is pushed into every peer's receive area by
+    the copy engines over NVLink, arrival is signalled and awaited with stream memory operations (capi.P2PExchange,
+    csrc/exchange.cu) -- no SM is taken from the search kernel of the next batch, and nothing spins while the slowest rank
+    catches up.  One object serves all steps; `views(depth)` hands out the per-slot objects PipelinedShardSearch cycles
+    (each with its own merged-output tensors)."""
+
+    def __init__(self, nq, k, device, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import capi
+        self.torch, self.nq, self.k = torch, nq, k
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.block = (nq * k * 12 + 7) // 8 * 8
+        self.step_no = 0
+
+        def gather(desc):
+            mine = torch.frombuffer(bytearray(desc), dtype=torch.uint8).to(device)
+            allt = torch.empty(self.world * len(desc), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allt, mine, group=group)
+            return bytes(allt.cpu().numpy().tobytes())
+
+        self.x = capi.P2PExchange(device.index if device.index is not None else torch.cuda.current_device(), self.world,
+                                  self.rank, self.block, gather)
+        self.device = device
+
+    class _View:
+        def __init__(self, parent):
+            t = parent.torch
+            self.p = parent
+            self.out_l = t.empty((parent.nq, parent.k), dtype=t.int64, device=parent.device)
+            self.out_d = t.empty((parent.nq, parent.k), dtype=t.float32, device=parent.device)
+            self.step = 0
+            self.allb = 0
+
+        def local_ptrs(self):
+            """starts the next step: device addresses the shard's search must write its labels / dists to"""
+            self.p.step_no += 1
+            self.step = self.p.step_no
+            mine, self.allb = self.p.x.slot(self.step)
+            return mine, mine + self.p.nq * self.p.k * 8
+
+        def exchange_and_merge(self, stream, out_ptrs=None):
+            from . import capi
+            self.p.x.step(self.step, stream)
+            ol, od = out_ptrs if out_ptrs else (self.out_l.data_ptr(), self.out_d.data_ptr())
+            capi.merge_topk_packed_device(self.allb, self.p.block, self.p.world, self.p.nq, self.p.k, ol, od, stream)
+            return self.out_l, self.out_d
+
+    def views(self, depth):
+        return [P2PShardExchange._View(self) for _ in range(depth)]
 
 
 class PipelinedShardSearch:
@@ -123,16 +178,22 @@ class PipelinedShardSearch:
     behind compute instead of serialising with it.  ``depth`` result blocks are cycled; a block is reused only after
     its exchange finished (event wait, no host sync)."""
 
-    def __init__(self, index, nq, k, device, depth=2, group=None):
+    def __init__(self, index, nq, k, device, depth=2, group=None, exchange="nccl"):
         import torch
         self.torch, self.index, self.nq, self.k = torch, index, nq, k
-        self.slots = [PackedShardExchange(nq, k, device, group) for _ in range(depth)]
+        if exchange == "p2p":  # copy-engine pushes + stream memory flags instead of the NCCL all_gather
+            self.p2p = P2PShardExchange(nq, k, device, group)
+            self.slots = self.p2p.views(depth)
+        else:
+            self.slots = [PackedShardExchange(nq, k, device, group) for _ in range(depth)]
         self.done = [None] * depth
         self.side = torch.cuda.Stream(device=device, priority=-1)
         self.i = 0
 
-    def submit(self, d_queries, ef, d_work=0):
-        """enqueue one batch; returns (labels, dists, event) -- the tensors are valid once ``event`` completed"""
+    def submit(self, d_queries, ef, d_work=0, out_ptrs=None):
+        """enqueue one batch; returns (labels, dists, event) -- the tensors are valid once ``event`` completed.
+        ``d_queries`` / ``out_ptrs`` may be addresses of page-locked host memory (device-accessible): the search kernel
+        then reads the queries and the merge kernel stores the merged rows over PCIe themselves."""
         torch = self.torch
         main = torch.cuda.current_stream()
         j = self.i % len(self.slots)
@@ -147,7 +208,7 @@ class PipelinedShardSearch:
         self.last_searched = searched
         self.side.wait_event(searched)
         with torch.cuda.stream(self.side):
-            out_l, out_d = slot.exchange_and_merge(self.side.cuda_stream)
+            out_l, out_d = slot.exchange_and_merge(self.side.cuda_stream, out_ptrs)
             ev = torch.cuda.Event()
             ev.record(self.side)
         self.done[j] = ev
@@ -163,8 +224,13 @@ class PipelinedShardSearch:
         serving loop that keeps ``depth`` batches in flight overlaps all of them.  Returns the event after which
         ``h_labels`` / ``h_dists`` hold the merged rows of this batch."""
         torch = self.torch
+        import os
+        if (h_queries.is_pinned() and h_labels.is_pinned() and h_dists.is_pinned()
+                and os.environ.get("B200HNSW_ZEROCOPY", "1") != "0"):
+            # page-locked buffers are device-accessible: no staging copies, no copy streams
+            return self.submit(h_queries.data_ptr(), ef, out_ptrs=(h_labels.data_ptr(), h_dists.data_ptr()))[2]
         if not hasattr(self, "_h2d"):
-            dev = self.slots[0].mine.device
+            dev = self.slots[0].out_l.device
             self._h2d = torch.cuda.Stream(device=dev)
             self._d2h = torch.cuda.Stream(device=dev)
             self._dq = [torch.empty(tuple(h_queries.shape), dtype=torch.float32, device=dev) for _ in self.slots]
