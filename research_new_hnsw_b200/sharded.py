@@ -199,7 +199,9 @@ class PipelinedShardSearch:
         j = self.i % len(self.slots)
         self.i += 1
         slot = self.slots[j]
-        if self.done[j] is not None:
+        if self.done[j] is not None and not self.done[j].query():
+            # (only when the exchange that last used this slot is still running: a wait between two search launches
+            # would also take away their programmatic overlap)
             main.wait_event(self.done[j])
         pl, pd = slot.local_ptrs()
         self.index.searchKnnDevice(d_queries, self.nq, self.k, ef, pl, pd, 0, d_work, main.cuda_stream)

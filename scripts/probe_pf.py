@@ -49,8 +49,13 @@ for ef in efs:
             idx.searchKnnDevice(dq[s % 4].data_ptr(), nq, k, ef, ol.data_ptr(), od.data_ptr(), 0, 0, st)
         torch.cuda.synchronize()
         e0.record()
+        evs = []
         for s in range(20):
+            if os.environ.get("PROBE_WAIT") and len(evs) >= 2:   # a wait on an event that completed long ago
+                torch.cuda.current_stream().wait_event(evs[-2])
             idx.searchKnnDevice(dq[s % 4].data_ptr(), nq, k, ef, ol.data_ptr(), od.data_ptr(), 0, 0, st)
+            if os.environ.get("PROBE_EVENTS"):                    # an event record between consecutive launches
+                ev = torch.cuda.Event(); ev.record(); evs.append(ev)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1) / 20)
