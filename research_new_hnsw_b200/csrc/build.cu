@@ -24,8 +24,10 @@
 // slots of every batch) is computed up front and uploaded ONCE; per batch the host only enqueues three kernels and
 // a 4-byte memset.  build_reverse_kernel is persistent (grid-stride over the device-side count of touched lists).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -59,15 +61,28 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
     } staged_flag{*this};
     HostImage &m = host;
     std::vector<uint32_t> updates, revived;  // revived: slots that were marked deleted until this call
+    // Pass 1 (sequential: label map, level generator, slot assignment) records which record each new row goes to;
+    // pass 2 writes the records of the new points with several threads (first touch of ~0.8 KB per point dominates a
+    // million-point addPoints otherwise); rows that overwrite a point staged by this very call are applied after it,
+    // in call order.
+    const size_t cur0 = m.cur;
+    std::vector<size_t> fresh_row;  // row of X behind slot cur0 + j
+    fresh_row.reserve(n);
+    std::vector<std::pair<size_t, uint32_t>> later;  // (row of X, slot) for labels repeated inside this call
+    auto write_rows = [&]() {  // also on the error returns below: the rows accepted so far stay added
+        stage_records(X, labels, cur0, fresh_row);
+        for (const auto &u : later) memcpy(m.rec(u.second) + m.off_data, X + u.first * m.dim, m.dim * 4);
+    };
     for (size_t i = 0; i < n; i++) {
         const uint64_t lab = labels ? labels[i] : (uint64_t)m.cur;
         auto known = m.label_lookup.find(lab);
         if (known != m.label_lookup.end()) {
             // existing label: update instead of insert (hnswalg.h:1157-1174)
             const uint32_t c = known->second;
-            if (m.deleted(c)) {
+            if (c < cur0 && m.deleted(c)) {  // (records of this call's own new points are written in pass 2)
                 if (prm.allow_replace_deleted) {
                     set_error("Can't use addPoint to update deleted elements if replacement of deleted elements is enabled.");
+                    write_rows();
                     return B200HNSW_E_STATE;
                 }
                 *((unsigned char *)m.rec(c) + 2) &= (unsigned char)~1;  // unmarkDeletedInternal
@@ -75,14 +90,15 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
                 flags_dirty = true;
                 if (c < linked) revived.push_back(c);
             }
-            memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
+            if (c >= cur0) later.emplace_back(i, c);
+            else memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
             if (c < linked) updates.push_back(c);  // a staged point is simply linked with its new vector later
             continue;
         }
         if (replace_deleted && m.num_deleted > 0) {
             // vacant place: a deleted element takes the new label and vector (hnswalg.h:965-992)
             size_t c = replace_scan < m.cur ? replace_scan : 0;
-            while (!m.deleted(c)) c = c + 1 < m.cur ? c + 1 : 0;  // num_deleted > 0: terminates
+            while (c >= cur0 || !m.deleted(c)) c = c + 1 < cur0 ? c + 1 : 0;  // num_deleted > 0: terminates
             replace_scan = c + 1;
             uint64_t old_label;
             memcpy(&old_label, m.rec(c) + m.off_label, 8);
@@ -98,16 +114,16 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
         }
         if (m.cur >= m.max_elements) {
             set_error("The number of elements exceeds the specified limit");
+            write_rows();
             return B200HNSW_E_CAPACITY;
         }
         const size_t c = m.cur++;
         m.label_lookup[lab] = (uint32_t)c;
         const int level = m.random_level();
         m.levels[c] = level;
-        memset(m.rec(c), 0, m.size_data);
-        memcpy(m.rec(c) + m.off_label, &lab, 8);
-        memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
-        m.upper[c].assign((size_t)level * m.size_links, 0);
+        fresh_row.push_back(i);
+        if (level > 0) m.upper[c].assign((size_t)level * m.size_links, 0);
+        else m.upper[c].clear();
         if (c == 0) {
             m.enterpoint = 0;
             m.maxlevel = level;
@@ -116,7 +132,31 @@ int HnswIndex::add_batch(const float *X, const uint64_t *labels, size_t n, bool 
             m.maxlevel = level;
         }
     }
+    write_rows();
     return updates.empty() ? 0 : relink_points(std::move(updates), revived);
+}
+
+// Level-0 records of the new points [cur0, cur0 + rows.size()): zeroed header and link list, vector, label.
+void HnswIndex::stage_records(const float *X, const uint64_t *labels, size_t cur0, const std::vector<size_t> &rows) {
+    HostImage &m = host;
+    const size_t cnt = rows.size();
+    auto fill = [&](size_t a, size_t b) {
+        for (size_t j = a; j < b; j++) {
+            const size_t c = cur0 + j, i = rows[j];
+            const uint64_t lab = labels ? labels[i] : (uint64_t)c;
+            memset(m.rec(c), 0, m.off_data);
+            memcpy(m.rec(c) + m.off_data, X + i * m.dim, m.dim * 4);
+            memcpy(m.rec(c) + m.off_label, &lab, 8);
+        }
+    };
+    size_t nt = std::min<size_t>(std::min<size_t>(std::thread::hardware_concurrency(), 8), cnt / 16384);
+    if (nt <= 1) {
+        fill(0, cnt);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++) th.emplace_back(fill, cnt * t / nt, cnt * (t + 1) / nt);
+    for (auto &t : th) t.join();
 }
 
 // updatePoint (hnswalg.h:995-1139) for points that are already part of the device graph.  Per group of points: the new
@@ -343,10 +383,11 @@ int HnswIndex::prepare_build(void *args, size_t max_batch, size_t *max_lists_out
     }
     const size_t bufcap = nb ? 2 * m.efc : m.efc;
     // construction searches evaluate ~40 * efc nodes; a table smaller than that is rebuilt from the candidate buffer
-    // when it fills (re-evaluations only, same graph) and lets more CTAs share an SM: measured at C5 (efc = 200),
-    // construction-search time 1470 ms with 8192 slots (6 CTAs per SM) vs 1271 ms with 4096 (10 CTAs, +9 % evaluations)
+    // when it fills (re-evaluations only, same graph) and lets more CTAs share an SM: measured at C5 (efc = 200) with
+    // 128-thread CTAs, construction-search time 1470 ms with 8192 slots (6 CTAs per SM) vs 1271 ms with 4096; with
+    // 64-thread CTAs 1203 ms (4096) / 924 ms (2048, 16 CTAs per SM, +5 % evaluations) / 976 ms (1024, +8 %)
     {
-        size_t want = std::min<size_t>(env_size("B200HNSW_BUILD_HASH", 4096), 32 * m.efc + 1024);
+        size_t want = std::min<size_t>(env_size("B200HNSW_BUILD_HASH", 2048), 32 * m.efc + 1024);
         want = std::max(want, 8 * (bufcap + list_cap) / 3 + 64);  // a hop must fit above the 5/8 rebuild mark
         a.hash_bits = 10;
         while ((1ull << a.hash_bits) < want) a.hash_bits++;
@@ -388,6 +429,10 @@ int HnswIndex::flush_locked() {
     const size_t ramp_ratio = env_size("B200HNSW_BUILD_RAMP_RATIO", std::min<size_t>(build_ratio, 8));
     const size_t ramp_until = env_size("B200HNSW_BUILD_RAMP_UNTIL", 65536);
 
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     // ---- upload vectors + labels of the staged points (records carry empty lists) ----
     {
         const size_t chunk = std::max<size_t>(1, std::min<size_t>(n_new, (size_t)(256u << 20) / rec));
@@ -414,6 +459,7 @@ int HnswIndex::flush_locked() {
         int rc16 = sync_bf16(linked, n_new);
         if (rc16) return rc16;
     }
+    const double ms_upload = since(t_start);
     // ---- upper-level list slots of the staged points (appended after the existing ones) ----
     {
         std::vector<uint32_t> base(n_new, kEmpty);
@@ -502,6 +548,7 @@ int HnswIndex::flush_locked() {
     B200_CUDA_OK(cudaMemcpyAsync(d_lp, lp_all.data(), lp_all.size() * 4, cudaMemcpyHostToDevice, stream));
     B200_CUDA_OK(cudaMemcpyAsync(d_ll, ll_all.data(), ll_all.size() * 4, cudaMemcpyHostToDevice, stream));
 
+    const double ms_plan = since(t_start) - ms_upload;
     cudaEvent_t e0, e1;
     B200_CUDA_OK(cudaEventCreate(&e0));
     B200_CUDA_OK(cudaEventCreate(&e1));
@@ -541,8 +588,9 @@ int HnswIndex::flush_locked() {
                     cudaEventElapsedTime(&ms, prof->ev[i + kx], prof->ev[i + kx + 1]);
                     t[kx] += ms;
                 }
-            fprintf(stderr, "[b200hnsw build profile] %zu batches: search %.1f ms, link %.1f ms, reverse %.1f ms\n",
-                    prof->ev.size() / 4, t[0], t[1], t[2]);
+            fprintf(stderr, "[b200hnsw build profile] %zu batches: search %.1f ms, link %.1f ms, reverse %.1f ms; host: upload "
+                    "%.1f ms, plan %.1f ms, flush so far %.1f ms\n",
+                    prof->ev.size() / 4, t[0], t[1], t[2], ms_upload, ms_plan, since(t_start));
             for (cudaEvent_t e : prof->ev) cudaEventDestroy(e);
             prof->ev.clear();
         }

@@ -9,11 +9,18 @@
 
 namespace b200 {
 
+// Threads per CTA of the build kernels.  64-thread teams keep 16 construction searches resident per SM (64 registers
+// per thread) instead of 8: measured at C5 with a 2048-slot visited table, construction search 924 ms vs 1179 ms
+// (128 threads, 4096 slots), link 244 vs 252 ms, reverse 63 vs 77 ms (gpurun_out/s2_build_team.log).
 #ifndef B200_BUILD_TEAM
-#define B200_BUILD_TEAM 128
+#define B200_BUILD_TEAM 64
 #endif
-constexpr int kTeam = B200_BUILD_TEAM;  // threads per CTA of the build kernels
+constexpr int kTeam = B200_BUILD_TEAM;
 constexpr uint32_t kCapIn = 32;  // incoming reverse edges kept per list and batch
+#ifndef B200_PRUNE_AHEAD
+#define B200_PRUNE_AHEAD 8
+#endif
+constexpr int kPruneAhead = B200_PRUNE_AHEAD;  // heuristic_prune: candidate rows prefetched into L2 this many rounds ahead
 
 struct BuildArgs {
     float4 *vec;
@@ -69,16 +76,19 @@ __device__ __forceinline__ void load_row(float4 (&v)[CPL], const float4 *row, ui
 }
 
 // Construction search for one new point: CTA b handles point first + b on all of its levels.
-template <int LPV, int CPL, int METRIC, bool UPD, bool NB>
+// FULL: rows are exactly LPV * CPL 128-bit chunks, so every "chunk index < d4" test of the gathers folds at compile
+// time (same device as hnsw_search_kernel's FULL instantiation).
+template <int LPV, int CPL, int METRIC, bool UPD, bool NB, bool FULL = false>
 __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) {
     extern __shared__ __align__(16) unsigned char smem[];
     const uint32_t list_cap = p.maxM0 > p.maxM ? p.maxM0 : p.maxM;
     const uint32_t bufcap = NB ? 2 * p.efc : p.efc;
-    const SearchSmem L(bufcap, list_cap, p.d4, p.hash_bits);
+    const uint32_t d4 = FULL ? (uint32_t)(LPV * CPL) : p.d4;
+    const SearchSmem L(bufcap, list_cap, d4, p.hash_bits);
     __shared__ int s_ints[kTeamInts];
     TeamCtx c;
     c.bind(smem, L, s_ints, p.hash_bits);
-    GraphView g{p.vec, p.links0, p.up_base, p.links_up, p.d4, p.maxM, p.maxM0};
+    GraphView g{p.vec, p.links0, p.up_base, p.links_up, d4, p.maxM, p.maxM0};
     g.pf = p.pf;
 
     const int tid = threadIdx.x;
@@ -88,12 +98,12 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
     const int plevel = p.plevel[pid];
 
     float4 q[CPL];
-    load_row<LPV, CPL>(q, p.vec + (size_t)pid * p.d4, p.d4, sub);
+    load_row<LPV, CPL>(q, p.vec + (size_t)pid * d4, d4, sub);
     if (tid == 0) { *c.s_cnt = 0; *c.s_acc = 0; *c.s_next = 0; c.ids[0] = p.entry; }
     __syncthreads();
     WorkCounters w;
     uint32_t cur = p.entry;
-    eval_list<kTeam, LPV, CPL, METRIC>(q, g.vec, p.d4, c.ids, 1, c.dist, grp, sub);
+    eval_list<kTeam, LPV, CPL, METRIC>(q, g.vec, d4, c.ids, 1, c.dist, grp, sub);
     __syncthreads();
     float curdist = c.dist[0];
     w.D += 1;
@@ -155,10 +165,17 @@ __device__ __forceinline__ int heuristic_prune(const GraphView &g, const uint64_
     }
     int ns = 0;
     float4 v[CPL], vn[CPL];
+    // rows of the candidates kPruneAhead rounds ahead -> L2, so the register prefetch of the NEXT candidate below is an L2
+    // hit instead of a DRAM round trip per round (one thread per 128-byte line)
+    const uint32_t row_bytes = g.d4 * 16, lpr = (row_bytes + kPfLine - 1) / kPfLine;
+    for (uint32_t i = tid; i < (uint32_t)min(n, kPruneAhead) * lpr; i += kTeam)
+        prefetch_l2((const char *)(g.vec + (size_t)((uint32_t)cand[i / lpr] & kIdMask) * g.d4) + (i % lpr) * kPfLine);
     load_row<LPV, CPL>(v, g.vec + (size_t)((uint32_t)cand[0] & kIdMask) * g.d4, g.d4, sub);
     for (int ci = 0; ci < n && ns < Mlimit; ci++) {
         const uint64_t key = cand[ci];
         const float dq = ord2f((uint32_t)(key >> 32));
+        if (ci + kPruneAhead < n && (uint32_t)tid < lpr)
+            prefetch_l2((const char *)(g.vec + (size_t)((uint32_t)cand[ci + kPruneAhead] & kIdMask) * g.d4) + tid * kPfLine);
         if (ci + 1 < n) load_row<LPV, CPL>(vn, g.vec + (size_t)((uint32_t)cand[ci + 1] & kIdMask) * g.d4, g.d4, sub);
         eval_list<kTeam, LPV, CPL, METRIC, true>(v, g.vec, g.d4, ids, ns, dist, grp, sub);
         evals += ns;
@@ -359,11 +376,21 @@ static int run_batch(const BuildArgs &a, size_t smem_search, size_t smem_link, c
         B200_CUDA_OK(cudaFuncGetAttributes(&fa, build_search_kernel<LPV, CPL, METRIC, UPD, NB>));
         B200_CUDA_OK(cudaFuncSetAttribute(build_search_kernel<LPV, CPL, METRIC, UPD, NB>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+        if constexpr (!UPD && !NB)
+            B200_CUDA_OK(cudaFuncSetAttribute(build_search_kernel<LPV, CPL, METRIC, UPD, NB, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
         configured[d] = true;
     }
     BuildProfile *prof = build_profile();
     if (prof) prof->mark(st);
-    build_search_kernel<LPV, CPL, METRIC, UPD, NB><<<a.batch, kTeam, smem_search, st>>>(a);
+    if constexpr (!UPD && !NB) {  // the bulk-build family also exists with the row length folded in
+        if (a.d4 == (uint32_t)(LPV * CPL))
+            build_search_kernel<LPV, CPL, METRIC, UPD, NB, true><<<a.batch, kTeam, smem_search, st>>>(a);
+        else
+            build_search_kernel<LPV, CPL, METRIC, UPD, NB><<<a.batch, kTeam, smem_search, st>>>(a);
+    } else {
+        build_search_kernel<LPV, CPL, METRIC, UPD, NB><<<a.batch, kTeam, smem_search, st>>>(a);
+    }
     if (prof) prof->mark(st);
     build_link_kernel<LPV, CPL, METRIC, UPD><<<a.lists, kTeam, smem_link, st>>>(a);
     if (prof) prof->mark(st);

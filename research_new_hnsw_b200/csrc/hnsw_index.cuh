@@ -119,6 +119,7 @@ struct HnswIndex {
                            uint32_t *counts, uint32_t *work, const uint8_t *allowed);
     // build.cu: addPoint staging and the batched GPU graph build
     int add_batch(const float *X, const uint64_t *labels, size_t n, bool replace_deleted = false);
+    void stage_records(const float *X, const uint64_t *labels, size_t cur0, const std::vector<size_t> &rows);
     size_t replace_scan = 0;  // where the search for a deleted slot resumes (replace_deleted)
     int flush();              // takes `rw` exclusively when there is something to link
     int flush_locked();       // caller holds `rw` exclusively
