@@ -588,6 +588,19 @@ int HnswIndex::flush_locked() {
                     cudaEventElapsedTime(&ms, prof->ev[i + kx], prof->ev[i + kx + 1]);
                     t[kx] += ms;
                 }
+            {   // the last batch alone (full-size graph) and the ramp-up (batches below the maximum size)
+                const size_t nb_ = prof->ev.size() / 4;
+                float tl[3] = {0, 0, 0}, ramp = 0;
+                for (int kx = 0; kx < 3 && nb_; kx++) cudaEventElapsedTime(&tl[kx], prof->ev[(nb_ - 1) * 4 + kx], prof->ev[(nb_ - 1) * 4 + kx + 1]);
+                for (size_t i = 0; i < nb_ && i < plan.size(); i++)
+                    if (plan[i].batch < max_batch) {
+                        float ms = 0;
+                        cudaEventElapsedTime(&ms, prof->ev[i * 4], prof->ev[i * 4 + 3]);
+                        ramp += ms;
+                    }
+                fprintf(stderr, "[b200hnsw build profile] last batch (%u points): search %.2f ms, link %.2f ms, reverse %.2f ms; "
+                        "batches below %zu points: %.1f ms\n", plan.empty() ? 0u : plan.back().batch, tl[0], tl[1], tl[2], max_batch, ramp);
+            }
             fprintf(stderr, "[b200hnsw build profile] %zu batches: search %.1f ms, link %.1f ms, reverse %.1f ms; host: upload "
                     "%.1f ms, plan %.1f ms, flush so far %.1f ms\n",
                     prof->ev.size() / 4, t[0], t[1], t[2], ms_upload, ms_plan, since(t_start));

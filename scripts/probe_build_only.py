@@ -13,4 +13,13 @@ for rep in range(2):
     print("%s rep %d: %.2f s (%.0f pts/s), addPoints %.2f s, flush events %.0f ms, D/pt %.1f, dropped reverse edges %d" % (
         os.path.basename(os.environ.get("B200HNSW_LIB", "head")), rep, sec, len(X) / sec, t_add, st["last_kernel_ms"],
         st["dist_evals"] / len(X), st["dropped_reverse_edges"]), flush=True)
+    if rep == 1 and os.environ.get("PROBE_SEARCH_AFTER"):
+        # the same amount of traversal as one full build batch, through the search kernel (for comparison)
+        Qb = X[-16384:]
+        for ef in (200,):
+            for _ in range(3):
+                r = g.searchKnnBatch(Qb, 10, ef=ef, work=True)
+            s2 = g.stats()
+            print("search kernel on the built graph: 16384 queries ef=%d: %.2f ms, D/q %.0f, H0/q %.1f, resets %d" % (
+                ef, s2["last_kernel_ms"], s2["dist_evals"] / len(Qb), s2["hops_base"] / len(Qb), s2["visited_resets"]), flush=True)
     del g
