@@ -238,6 +238,11 @@ int HnswIndex::upload_flags(const uint8_t *allowed, const uint32_t *extra, size_
     for (size_t i = 0; i < host.cur; i++) f[i] = (host.deleted(i) || (allowed && !allowed[i])) ? 1 : 0;
     for (size_t i = 0; i < n_extra; i++)
         if (extra[i] < host.cur) f[extra[i]] = 1;
+    {
+        size_t rej = 0;
+        for (uint8_t v : f) rej += v;
+        flags_rejected = rej;  // sizes the candidate buffer of the non-bare search (launch_search)
+    }
     // calls that pass the same filter over and over (the shim evaluates a functor into the same verdicts each time) do
     // not pay the upload again: the device array is only rewritten when its content changes
     uint64_t h = 0xcbf29ce484222325ull ^ (uint64_t)host.cur;
@@ -341,7 +346,21 @@ int HnswIndex::launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, 
     a.vec16 = bf16 ? dev.vec16 : nullptr;
     a.d16 = (uint32_t)dev.d16;
     a.flags = nonbare ? dev.flags : nullptr;
-    a.bufcap = (uint32_t)(nonbare ? 2 * efx : efx);
+    a.bufcap = (uint32_t)efx;
+    if (nonbare) {
+        // The reference keeps EVERY visited element inside the bound in candidate_set, deleted or not (hnswalg.h:395-408);
+        // only the non-deleted ones count towards ef.  With a fraction f of the elements rejected (deleted or filtered
+        // out) about ef * f / (1 - f) rejected entries sit inside the bound of a full result set: the buffer holds three
+        // times that expectation (at least ef, at most 15 * ef) on top of the ef results, as far as shared memory allows.
+        const double f = std::min(0.999, (double)flags_rejected / (double)std::max<size_t>(linked, 1));
+        size_t extra = (size_t)(3.0 * (double)efx * f / (1.0 - f)) + 32;
+        extra = std::min(std::max(extra, efx), 15 * efx);
+        size_t cap = efx + extra;
+        while (cap > 2 * efx &&
+               SearchSmem((uint32_t)cap, (uint32_t)list_cap, a.d4, pick_hash_bits(cap, list_cap, team)).total > 96 * 1024)
+            cap = std::max(2 * efx, cap * 3 / 4);
+        a.bufcap = (uint32_t)cap;
+    }
     a.hash_bits = pick_hash_bits(a.bufcap, list_cap, team);
     {
         static const int pf_env = getenv("B200HNSW_PF") ? atoi(getenv("B200HNSW_PF")) : -1;

@@ -67,6 +67,7 @@ struct HnswIndex {
     int dev_maxlevel = -1;
     bool mirror_dirty = false;          // device link lists are newer than the host mirror
     std::atomic<bool> flags_dirty{true};  // delete marks changed since the last upload
+    size_t flags_rejected = 0;          // elements marked in the last uploaded flag array (deleted or filtered out)
     BuildScratch bld;
     cudaStream_t stream = nullptr;      // build / update stream
     // pool of search contexts (host-pointer search path)

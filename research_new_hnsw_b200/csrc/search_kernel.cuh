@@ -44,7 +44,7 @@ struct SearchArgs {
     const uint8_t *flags;     // [n] bit 0 = deleted (hnswalg.h:934-937); null when nothing is deleted
     const uint4 *vec16;       // [n][d16] bf16 rows (storage variant) or null
     uint32_t d16;
-    uint32_t bufcap;          // entries per candidate buffer: ef (bare-bone) or 2*ef (deleted elements present)
+    uint32_t bufcap;          // entries per candidate buffer: ef (bare-bone), or ef + room for the rejected entries inside the bound
     uint32_t n, entry;
     int32_t maxlevel;
     uint32_t dim, d4, maxM, maxM0;
@@ -430,7 +430,8 @@ __device__ __forceinline__ void greedy_level(const TeamCtx &c, const float4 (&q)
 // deleted nodes are traversed but never enter top_candidates.  They stay in the same sorted buffer with bit 30 set;
 // only non-deleted entries count towards ef, the bound is the ef-th non-deleted distance, and everything behind that
 // entry is dropped after each merge (the reference would stop at the first such candidate, :346-358).  The buffer
-// holds up to 2*ef entries; more than ef deleted nodes inside the bound lose their farthest members.
+// holds bufcap entries (sized by launch_search from the rejected fraction); rejected entries beyond it lose their
+// farthest members.
 template <int TEAM, int LPV, int CPL, int METRIC, bool NB = false, int STORE = 0>
 __device__ __forceinline__ void beam_level(const TeamCtx &c, const float4 (&q)[STORE ? (CPL + 1) / 2 * 2 : CPL],
                                            const GraphView &g, int level, uint32_t ef, uint32_t cur, float curdist,

@@ -182,10 +182,9 @@ def test_deleted_elements_non_bare_search(lib, orc, graphs, name, frac):
         c = cpu.search(s["Q"], 10, ef)
         assert not (set(r["labels"].ravel().tolist()) & dead_set)
         same = _same_sets(r["labels"], c["labels"]).mean()
-        if frac <= 0.2:
-            _check(r, c, (name, ef, "deleted"))
-        else:  # more deleted nodes than the 2*ef buffer can carry inside the bound: documented approximation
-            assert same >= 0.9, (name, ef, same)
+        # the candidate buffer is sized from the deleted fraction (3x the expected number of deleted entries inside the
+        # bound), so the 99 % bar holds at 50 % deleted as well
+        _check(r, c, (name, ef, "deleted", same))
     with pytest.raises(lib.B200Error, match="already deleted"):
         idx.markDelete(int(dead[0]))
     for l in dead.tolist():
