@@ -45,11 +45,23 @@ constexpr int kGThreads = 192;
 constexpr uint32_t kStageA = kGM * kGK * 2;   // 16 KB
 constexpr uint32_t kStageB = kGN * kGK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageA + kStageB;
+// CTA-pair variant (tcgen05 cta_group::2): the pair multiplies 256 rows x 256 queries per instruction; each CTA stages its
+// own 128 rows of A and HALF of the query tile (128 queries), the tensor cores read the other half from the partner's
+// shared memory -- a third fewer bytes per tile from L2 into each SM (the single-CTA mainloop pulls 14.6-16.8 TB/s
+// through the L2->SM path, profiles/r02_bf_c4_kernels_ncu_full.txt), and the smaller stage buys a 6-deep ring.
+constexpr int kGStages2 = 6;
+constexpr uint32_t kStageB2 = (kGN / 2) * kGK * 2;   // 16 KB
+constexpr uint32_t kStageBytes2 = kStageA + kStageB2;
 constexpr int kQCap = 512;     // entries of one epilogue warp's hit queue (pass 2)
 constexpr uint32_t kGemmSmem = kGStages * kStageBytes + 1024 /*align*/ + 8192 /*barriers + per-tile tables*/ +
                                4 * 2 * kQCap * 4 /*hit queues*/;
+static_assert(kGStages2 * kStageBytes2 == kGStages * kStageBytes, "both variants share one shared-memory carve-up");
 constexpr float kErrC = 0.0078125f + 0.000244140625f;   // 2^-7 + 2^-12
 constexpr float kErrDelta = 4e-6f;
+#ifndef B200_BF_DEFAULT_CG
+#define B200_BF_DEFAULT_CG 1
+#endif
+constexpr int kDefaultCG = B200_BF_DEFAULT_CG;
 
 struct GemmArgs {
     const float *xn2;       // [rows] squared norms (fp32)
@@ -67,6 +79,40 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// CTA-pair forms: the barrier operand is a shared::cluster address (the leader CTA's barrier for loads)
+__device__ __forceinline__ void tma_load_2d_pair(void *dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {  // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar) {  // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -99,6 +145,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 }
 // Instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 at bit 17, M>>4 at bit 24.
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGN >> 3) << 17) | ((uint32_t)(kGM >> 4) << 24);
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGN >> 3) << 17) | ((uint32_t)((2 * kGM) >> 4) << 24);
 
 // Hit queue of one epilogue warp: entries (column of the tile << 8 | row of the tile, value), all of the CURRENT tile.
 // 32 entries per step: their atomicAdds on the per-query counters are in flight together.
@@ -114,36 +161,52 @@ __device__ __forceinline__ void flush_queue(const GemmArgs &a, const uint32_t *q
     __syncwarp();
 }
 
-template <int METRIC, int MODE>
+// CG = 1: one CTA per 128-row panel.  CG = 2: launched in clusters of two CTAs (one TPC); the pair works on two
+// consecutive (sampled) panels and one query tile per item, rank 0 issues the cta_group::2 MMAs for both.
+template <int METRIC, int MODE, int CG = 1>
 __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmArgs a) {
+    constexpr int kNS = CG == 2 ? kGStages2 : kGStages;
+    constexpr uint32_t kSB = CG == 2 ? kStageBytes2 : kStageBytes;
     extern __shared__ unsigned char smem_raw[];
     // 1024-byte alignment (SWIZZLE_128B) as an OFFSET into the shared array: casting through an integer would lose the
     // address space and turn every table / queue access of the epilogue into a generic load
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *tail = smem + kGStages * kStageBytes;
-    uint64_t *full = (uint64_t *)tail;            // [kGStages]
-    uint64_t *empty = full + kGStages;            // [kGStages]
-    uint64_t *tfull = empty + kGStages;           // [2]
+    uint64_t *full = (uint64_t *)tail;            // [kNS] (max 6)
+    uint64_t *empty = full + kGStages2;           // [kNS]
+    uint64_t *tfull = empty + kGStages2;          // [2]
     uint64_t *tempty = tfull + 2;                 // [2]
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t sampled = (a.panels + a.stride - 1) / a.stride;
-    const uint32_t items = sampled * a.qtiles;
+    // item = (panel or panel pair, query tile); the CTAs of a pair walk the same items
+    const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+    const uint32_t items = (CG == 2 ? (sampled + 1) / 2 : sampled) * a.qtiles;
+    const uint32_t it0 = CG == 2 ? blockIdx.x / 2 : blockIdx.x, it_step = CG == 2 ? gridDim.x / 2 : gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kGStages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        // CG = 2: `full` and `tempty` are only used in the leader (loads of both CTAs complete on the leader's barrier,
+        // the epilogue warps of both CTAs release the accumulators there); `empty` / `tfull` exist in both and receive
+        // the leader's multicast commits
+        for (int s = 0; s < kNS; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the partner's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -151,38 +214,50 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
-                const uint32_t p = (it / a.qtiles) * a.stride, t = it % a.qtiles;
+            for (uint32_t it = it0; it < items; it += it_step) {
+                const uint32_t p = ((it / a.qtiles) * CG + rank) * a.stride, t = it % a.qtiles;
                 for (uint32_t kc = 0; kc < a.kchunks; kc++) {
-                    mbar_wait(empty + stage, phase ^ 1);
-                    mbar_expect_tx(full + stage, kStageBytes);
-                    unsigned char *sa = smem + stage * kStageBytes;
-                    tma_load_2d(sa, &tmA, full + stage, (int)(kc * kGK), (int)(p * kGM));
-                    tma_load_2d(sa + kStageA, &tmB, full + stage, (int)(kc * kGK), (int)(t * kGN));
-                    if (++stage == kGStages) { stage = 0; phase ^= 1; }
+                    mbar_wait(empty + stage, phase ^ 1);  // (CG = 2: the pair's MMAs on this stage have retired)
+                    unsigned char *sa = smem + stage * kSB;
+                    if (CG == 2) {
+                        // both CTAs' boxes complete on the LEADER's barrier: 2 x (A half + B half) bytes per stage.  A panel
+                        // beyond the last one (odd count) is an out-of-bounds box: zero fill, full byte count.
+                        if (rank == 0) mbar_expect_tx(full + stage, 2 * kStageBytes2);
+                        const uint32_t fb = map_to_cta(full + stage, 0);
+                        tma_load_2d_pair(sa, &tmA, fb, (int)(kc * kGK), (int)(p * kGM));
+                        tma_load_2d_pair(sa + kStageA, &tmB, fb, (int)(kc * kGK), (int)(t * kGN + rank * (kGN / 2)));
+                    } else {
+                        mbar_expect_tx(full + stage, kStageBytes);
+                        tma_load_2d(sa, &tmA, full + stage, (int)(kc * kGK), (int)(p * kGM));
+                        tma_load_2d(sa + kStageA, &tmB, full + stage, (int)(kc * kGK), (int)(t * kGN));
+                    }
+                    if (++stage == kNS) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             uint32_t stage = 0, phase = 0, buf = 0, bphase = 0;
-            for (uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
+            for (uint32_t it = it0; it < items; it += it_step) {
                 mbar_wait(tempty + buf, bphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * kGN;
                 for (uint32_t kc = 0; kc < a.kchunks; kc++) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = smem_u32(smem + stage * kSB);
                     const uint64_t da = umma_desc(sa), db = umma_desc(sa + kStageA);
 #pragma unroll
-                    for (uint32_t k4 = 0; k4 < kGK / 16; k4++)  // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
-                        tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, kIdesc, (kc | k4) != 0);
-                    tc_commit(empty + stage);  // frees the smem stage when these MMAs retire
-                    if (++stage == kGStages) { stage = 0; phase ^= 1; }
+                    for (uint32_t k4 = 0; k4 < kGK / 16; k4++) {  // UMMA_K = 16 bf16 = 32 bytes = 2 descriptor units
+                        if (CG == 2) tc_mma_bf16_pair(d_tmem, da + 2 * k4, db + 2 * k4, kIdesc2, (kc | k4) != 0);
+                        else tc_mma_bf16(d_tmem, da + 2 * k4, db + 2 * k4, kIdesc, (kc | k4) != 0);
+                    }
+                    // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+                    if (CG == 2) tc_commit_pair(empty + stage); else tc_commit(empty + stage);
+                    if (++stage == kNS) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull + buf);  // accumulator complete
+                if (CG == 2) tc_commit_pair(tfull + buf); else tc_commit(tfull + buf);  // accumulator complete
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
             }
         }
@@ -208,7 +283,8 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         constexpr float alpha = METRIC == 1 ? -1.f : -2.f;
         uint32_t buf = 0, bphase = 0, tb = 0;
         float pB[2], pT[2];
-        uint32_t it = blockIdx.x;
+        uint32_t it = it0;
+        const uint32_t tempty_leader = CG == 2 ? map_to_cta(tempty, 0) : 0u;  // tempty[b] at + 8 * b
         if (it < items) {
             const uint32_t t = it % a.qtiles;
 #pragma unroll
@@ -222,9 +298,9 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         asm volatile("bar.sync 1, 128;" ::: "memory");
         uint32_t prev_pi = 0, prev_t = 0;
         bool have_prev = false;
-        for (; it < items; it += gridDim.x) {
-            const uint32_t pi = it / a.qtiles, p = pi * a.stride, t = it % a.qtiles;
-            const uint32_t nit = it + gridDim.x;
+        for (; it < items; it += it_step) {
+            const uint32_t pi = (it / a.qtiles) * CG + rank, p = pi * a.stride, t = it % a.qtiles;
+            const uint32_t nit = it + it_step;
             if (nit < items) {  // prefetch the next item's tables
                 const uint32_t nt = nit % a.qtiles;
 #pragma unroll
@@ -238,13 +314,13 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int j = et + e * 128;
-                    a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
+                    if (prev_pi < sampled) a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
                     s_min[(tb ^ 1) * kGN + j] = 0xFFFFFFFFu;
                 }
             }
             const float *B = s_B + tb * kGN, *T = s_T + tb * kGN;
             const uint32_t r = p * kGM + quarter * 32 + lane;
-            const bool rvalid = r < a.n && (!a.mask || a.mask[r]);
+            const bool rvalid = pi < sampled && r < a.n && (!a.mask || a.mask[r]);
             const float xn2 = rvalid ? a.xn2[r] : 0.f;
             const float xnorm = sqrtf(xn2);
             const float Ar = METRIC == 1 ? 0.f : (MODE == 0 ? (1.f + kErrDelta) : (1.f - kErrDelta)) * xn2;
@@ -344,7 +420,9 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
                 }
             }
             tc_fence_before();
-            if (lane == 0) mbar_arrive(tempty + buf);  // this warp is done with the accumulator
+            if (lane == 0) {  // this warp is done with the accumulator
+                if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * buf); else mbar_arrive(tempty + buf);
+            }
             if (++buf == 2) { buf = 0; bphase ^= 1; }
             if (MODE == 1) {
                 // The queue's entries are relative to this tile, so it is emptied before the next one -- but nobody has to
@@ -379,7 +457,7 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             tb ^= 1;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        if (MODE == 0 && have_prev) {
+        if (MODE == 0 && have_prev && prev_pi < sampled) {
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int j = et + e * 128;
@@ -391,9 +469,11 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();  // nobody leaves while the partner may still read its shared memory or signal it
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
 }
 
@@ -495,7 +575,13 @@ __global__ void __launch_bounds__(256) bf_kth_smem_kernel(const uint32_t *__rest
 constexpr int kRrThreads = 256;
 constexpr int kRrRows = 64;     // survivor rows staged per round of step C (4 threads per row)
 constexpr int kRrChunk4 = 32;   // 128-bit chunks of every row per stage (512 bytes)
-constexpr int kRrStride = 132;  // floats per staged row (stride = 4 mod 32 banks: the 8 rows x 4 lanes of a warp differ)
+// Staged layout of step C: tile[row][lane accumulator l][chunk] -- thread (row, l) finds the 32 floats it sums in one
+// stage (elements 4c + l of chunks c0..c0+31) CONTIGUOUS, so it reads them with 8 LDS.128 instead of 32 scalar loads
+// with address arithmetic (ncu of the previous layout: 1.23 G warp instructions per 10 k queries, 43 % issue-active --
+// the kernel was instruction-bound).  36 floats per (row, l): 16-byte reads of 8 consecutive threads fall into 8
+// different bank groups, and the staging stores of a warp (one chunk per lane) into 32 different banks.
+constexpr int kRrLane = 36;
+constexpr int kRrStride = 4 * kRrLane;  // floats per staged row
 
 template <int METRIC>
 __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
@@ -507,8 +593,9 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
                                                               float *__restrict__ out_d, uint32_t *__restrict__ out_c,
                                                               uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char sm[];
-    float *qs = (float *)sm;                              // [d4*4]
-    float *fd = qs + d4 * 4;                              // [cap] exact distances of the survivors
+    float *qs = (float *)sm;                              // [4][qstr] query, transposed: qs[l * qstr + c] = Q[4c + l]
+    const uint32_t qstr = ((d4 + 3) & ~3u) + 4;           // (+4: the four l-rows start in different bank groups)
+    float *fd = qs + 4 * qstr;                            // [cap] exact distances of the survivors
     uint32_t *ids = (uint32_t *)(fd + cap);               // [cap] candidate rows, later survivor rows
     uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [cap] (key + E, key - E) per candidate, later survivor labels
     float *tile = (float *)(cl + cap);                    // [max(kRrRows*kRrStride, cap)]
@@ -521,7 +608,7 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
         return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t i = tid; i < d4 * 4; i += kRrThreads) qs[i] = i < dim ? Q[(size_t)q * dim + i] : 0.f;
+    for (uint32_t i = tid; i < d4 * 4; i += kRrThreads) qs[(i & 3) * qstr + (i >> 2)] = i < dim ? Q[(size_t)q * dim + i] : 0.f;
     // ---- A: candidates and their error bounds ----
     const float q2 = qn2[q], qn = sqrtf(q2);
     float2 *he = (float2 *)cl;  // (key + E, key - E); cl[] proper is only written in step C
@@ -607,7 +694,8 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
 #pragma unroll
             for (int i = 0; i < kLd; i++) {
                 const uint32_t f = tid + kRrThreads * i;
-                *(float4 *)(tile + (f / kRrChunk4) * kRrStride + (f % kRrChunk4) * 4) = v[i];
+                float *dst = tile + (f / kRrChunk4) * kRrStride + (f % kRrChunk4);
+                dst[0] = v[i].x; dst[kRrLane] = v[i].y; dst[2 * kRrLane] = v[i].z; dst[3 * kRrLane] = v[i].w;
             }
             __syncthreads();
             if (c0 + kRrChunk4 < d4) issue(base, c0 + kRrChunk4);
@@ -615,10 +703,32 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
             if (rl < nb) {
                 const float *row = tile + rl * kRrStride;
                 const uint32_t pend = min((uint32_t)kRrChunk4, d4 - c0);
+                if (c0 + kRrChunk4 <= lane_chunks) {
+                    // the whole stage belongs to the lane accumulators: 32 terms, strictly in index order
+                    const float4 *x4 = (const float4 *)(row + al * kRrLane);
+                    const float4 *q4 = (const float4 *)(qs + al * qstr + c0);
+#pragma unroll
+                    for (int j = 0; j < kRrChunk4 / 4; j++) {
+                        const float4 xv = x4[j], qv = q4[j];
+                        if (METRIC == 0) {
+                            const float a0 = __fsub_rn(qv.x, xv.x), a1 = __fsub_rn(qv.y, xv.y), a2 = __fsub_rn(qv.z, xv.z),
+                                        a3 = __fsub_rn(qv.w, xv.w);
+                            acc = __fadd_rn(acc, __fmul_rn(a0, a0));
+                            acc = __fadd_rn(acc, __fmul_rn(a1, a1));
+                            acc = __fadd_rn(acc, __fmul_rn(a2, a2));
+                            acc = __fadd_rn(acc, __fmul_rn(a3, a3));
+                        } else {
+                            acc = __fadd_rn(acc, __fmul_rn(qv.x, xv.x));
+                            acc = __fadd_rn(acc, __fmul_rn(qv.y, xv.y));
+                            acc = __fadd_rn(acc, __fmul_rn(qv.z, xv.z));
+                            acc = __fadd_rn(acc, __fmul_rn(qv.w, xv.w));
+                        }
+                    }
+                } else
                 for (uint32_t part = 0; part < pend; part++) {
                     const uint32_t c = c0 + part;
                     if (c < lane_chunks) {
-                        const float x = row[part * 4 + al], qv = qs[4 * c + al];
+                        const float x = row[al * kRrLane + part], qv = qs[al * qstr + c];
                         float m;
                         if (METRIC == 0) {
                             const float a0 = __fsub_rn(qv, x);
@@ -630,7 +740,7 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
                     } else if (al == 0) {
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const float x = row[part * 4 + e], qv = qs[4 * c + e];
+                            const float x = row[e * kRrLane + part], qv = qs[e * qstr + c];
                             float m;
                             if (METRIC == 0) {
                                 const float a0 = __fsub_rn(qv, x);
@@ -760,7 +870,10 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
                               cudaStream_t st) {
     const size_t n = host.cur;
     const size_t panels = (n + kGM - 1) / kGM;
-    size_t stride = 4;
+    // Sampled bound pass: every stride-th panel.  The bound is the k-th smallest of the sampled panel minima, i.e. about the
+    // k * stride-th smallest key overall: a sparser sample costs candidates (680 -> 1350 -> 2750 per query at stride 4 /
+    // 8 / 16, C4) but saves 1/stride of a full GEMM.  Measured at C4 (gpurun_out/s2_bf_sample.log): 17.8 / 16.8 / 17.2 ms.
+    size_t stride = 8;
     if (const char *e = getenv("B200HNSW_BF_SAMPLE")) stride = std::max(1, atoi(e));
     while (stride > 1 && (panels + stride - 1) / stride < 2 * k) stride /= 2;
     if ((panels + stride - 1) / stride < k) return 1;
@@ -775,8 +888,9 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const size_t nq_pad = (nq + kGN - 1) / kGN * kGN;
     const size_t sampled = (panels + stride - 1) / stride;
     // candidate slots per query: k/f + the error band is the expectation; an overflowing batch is retried with 4x
-    size_t cap_c = std::max<size_t>(1536, 12 * k);
+    size_t cap_c = std::max<size_t>(2048, (stride >= 8 ? 20 : 12) * k);
     if (const char *e = getenv("B200HNSW_BF_CAP")) cap_c = std::max(256, atoi(e));
+    cap_c = (cap_c + 3) & ~(size_t)3;
     cap_c = std::max(cap_c, tz.cap_floor);
     cap_c = (cap_c + 3) / 4 * 4;  // the re-rank kernel's shared arrays stay 16-byte aligned
     if (nq_pad > tz.q_cap || cap_c != tz.cap) {
@@ -814,9 +928,12 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
                                                                            (__nv_bfloat16 *)tz.qb, tz.qn2);
     B200_CUDA_OK(cudaMemsetAsync(tz.cand_cnt, 0, nq_pad * 4, st));
     B200_CUDA_OK(cudaMemsetAsync(tz.overflow, 0, 4, st));
+    // CTA pairs (cta_group::2) unless B200HNSW_BF_CG=1
+    static const int cg = getenv("B200HNSW_BF_CG") ? atoi(getenv("B200HNSW_BF_CG")) : kDefaultCG;
+    const bool pair = cg == 2;
     CUtensorMap mA, mB;
     rc = make_map(&mA, tz.xb, tz.rows_pad, kp, kGM);
-    if (!rc) rc = make_map(&mB, tz.qb, nq_pad, kp, kGN);
+    if (!rc) rc = make_map(&mB, tz.qb, nq_pad, kp, pair ? kGN / 2 : kGN);
     if (rc) return rc;
     GemmArgs a{};
     a.xn2 = tz.xn2; a.tabB = tz.tabB; a.tabT = tz.tabT; a.panelmin = tz.panelmin; a.cand = (uint2 *)tz.cand;
@@ -830,6 +947,10 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         configured[device] = true;
     }
     int sms = 148;
@@ -839,9 +960,31 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     const unsigned tgrid = (unsigned)((nq_pad + 255) / 256);
     bf_tables_kernel<<<tgrid, 256, 0, st>>>(tz.qn2, tz.thr, (uint32_t)nq_pad, ip ? 1 : 0, 0, tz.tabB, tz.tabT);
     a.stride = (uint32_t)stride;
-    unsigned grid = (unsigned)std::min<size_t>((size_t)sms, sampled * a.qtiles);
-    if (ip) bf_gemm_kernel<1, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
-    else bf_gemm_kernel<0, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
+    // one persistent CTA per SM; pairs: one cluster of two per TPC, both CTAs walk the same items
+    auto launch_gemm = [&](int mode, size_t npanels) -> int {
+        if (!pair) {
+            const unsigned grid = (unsigned)std::min<size_t>((size_t)sms, npanels * a.qtiles);
+            if (ip) { if (mode) bf_gemm_kernel<1, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a); else bf_gemm_kernel<1, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a); }
+            else { if (mode) bf_gemm_kernel<0, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a); else bf_gemm_kernel<0, 0><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a); }
+            B200_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)std::min<size_t>((size_t)sms / 2, (npanels + 1) / 2 * a.qtiles));
+        cfg.blockDim = dim3(kGThreads);
+        cfg.dynamicSmemBytes = kGemmSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        auto *fn = ip ? (mode ? bf_gemm_kernel<1, 1, 2> : bf_gemm_kernel<1, 0, 2>) : (mode ? bf_gemm_kernel<0, 1, 2> : bf_gemm_kernel<0, 0, 2>);
+        B200_CUDA_OK(cudaLaunchKernelEx(&cfg, fn, mA, mB, a));
+        return 0;
+    };
+    rc = launch_gemm(0, sampled);
+    if (rc) return rc;
     mark();
     const size_t kth_smem = sampled * kKthQ * 4;
     if (kth_smem <= 160 * 1024) {
@@ -860,9 +1003,8 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     // pass 2: candidates from all panels
     bf_tables_kernel<<<tgrid, 256, 0, st>>>(tz.qn2, tz.thr, (uint32_t)nq_pad, ip ? 1 : 0, 1, tz.tabB, tz.tabT);
     a.stride = 1;
-    grid = (unsigned)std::min<size_t>((size_t)sms, panels * a.qtiles);
-    if (ip) bf_gemm_kernel<1, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
-    else bf_gemm_kernel<0, 1><<<grid, kGThreads, kGemmSmem, st>>>(mA, mB, a);
+    rc = launch_gemm(1, panels);
+    if (rc) return rc;
     mark();
     // exact re-rank
     const size_t dim = host.dim;
@@ -871,7 +1013,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     else if (dim > 16) lane_floats = dim >> 4 << 4;
     else if (dim > 4) lane_floats = dim >> 2 << 2;
     else lane_floats = 0;
-    const size_t rsm = d4 * 16 + cap_c * 4 + (cap_c + (cap_c & 1)) * 4 + cap_c * 8 +
+    const size_t rsm = ((((size_t)d4 + 3) & ~(size_t)3) + 4) * 16 + cap_c * 4 + (cap_c + (cap_c & 1)) * 4 + cap_c * 8 +
                        std::max<size_t>((size_t)kRrRows * kRrStride, cap_c) * 4;
     if (ip)
         launch_rerank<1>((unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim, (uint32_t)d4,
