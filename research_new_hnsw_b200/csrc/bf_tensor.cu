@@ -600,7 +600,9 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [cap] (key + E, key - E) per candidate, later survivor labels
     float *tile = (float *)(cl + cap);                    // [max(kRrRows*kRrStride, cap)]
     __shared__ uint32_t s_part[kRrThreads / 32];
+    __shared__ uint32_t s_hist[kRrThreads];
     __shared__ uint32_t s_cnt;
+    static_assert(kRrThreads == 256, "step B uses one histogram bin per thread");
     const uint32_t q = blockIdx.x;
     const uint32_t cnt = cand_cnt[q];
     if (cnt > cap) {  // candidate buffer overflowed: this batch is redone by the exact scan
@@ -629,22 +631,46 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     }
     if (tid == 0) s_cnt = 0;
     __syncthreads();
-    // ---- B: U2 = k-th smallest of key + E (bitwise binary search over ordered floats) ----
+    // ---- B: U2 = k-th smallest of key + E: radix select over the ordered-float bits, 8 bits per pass (4 passes of one
+    // shared-memory histogram each; the bit-by-bit search it replaces took 32 rounds of two block barriers) ----
     uint32_t prefix = 0;
     if (cnt > k) {
-        for (int bit = 31; bit >= 0; bit--) {
-            const uint32_t cval = prefix | ((1u << bit) - 1u);
-            uint32_t c = 0;
-            for (uint32_t i = tid; i < cnt; i += kRrThreads) c += f2ord(he[i].x) <= cval ? 1u : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) s_part[warp] = c;
+        uint32_t mask = 0, kk = k;  // kk-th smallest among the keys that match `prefix` under `mask`
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            s_hist[tid] = 0;  // kRrThreads == 256 bins
             __syncthreads();
-            uint32_t tot = 0;
-#pragma unroll
-            for (int w = 0; w < kRrThreads / 32; w++) tot += s_part[w];
+            for (uint32_t i = tid; i < cnt; i += kRrThreads) {
+                const uint32_t u = f2ord(he[i].x);
+                if ((u & mask) == prefix) atomicAdd(&s_hist[(u >> shift) & 255u], 1u);
+            }
             __syncthreads();
-            if (tot < k) prefix |= 1u << bit;
+            if (warp == 0) {  // lane l scans bins 8l .. 8l+7
+                uint32_t h[8], sum = 0;
+#pragma unroll
+                for (int b = 0; b < 8; b++) { h[b] = s_hist[lane * 8 + b]; sum += h[b]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const uint32_t before = incl - sum;
+                if (before < kk && kk <= incl) {  // exactly one lane
+                    uint32_t acc = before;
+                    int bin = 0;
+#pragma unroll
+                    for (int b = 0; b < 8; b++) {
+                        if (acc < kk && kk <= acc + h[b]) { bin = b; break; }
+                        acc += h[b];
+                    }
+                    s_part[0] = (uint32_t)(lane * 8 + bin);
+                    s_part[1] = kk - acc;
+                }
+            }
+            __syncthreads();
+            prefix |= s_part[0] << shift;
+            mask |= 255u << shift;
+            kk = s_part[1];
         }
     } else {
         prefix = 0xFFFFFFFFu;
@@ -929,7 +955,7 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     B200_CUDA_OK(cudaMemsetAsync(tz.cand_cnt, 0, nq_pad * 4, st));
     B200_CUDA_OK(cudaMemsetAsync(tz.overflow, 0, 4, st));
     // CTA pairs (cta_group::2) unless B200HNSW_BF_CG=1
-    static const int cg = getenv("B200HNSW_BF_CG") ? atoi(getenv("B200HNSW_BF_CG")) : kDefaultCG;
+    const int cg = getenv("B200HNSW_BF_CG") ? atoi(getenv("B200HNSW_BF_CG")) : kDefaultCG;
     const bool pair = cg == 2;
     CUtensorMap mA, mB;
     rc = make_map(&mA, tz.xb, tz.rows_pad, kp, kGM);

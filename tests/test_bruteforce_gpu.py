@@ -74,10 +74,14 @@ def test_k_larger_than_count(lib):
 
 @pytest.mark.parametrize("metric,n,d,k,nq", [(bind.L2, 40000, 128, 10, 300), (bind.IP, 30000, 768, 100, 130),
                                              (bind.L2, 20000, 100, 5, 257), (bind.IP, 33000, 30, 20, 64)])
-def test_tensor_core_path_is_exact(lib, orc, monkeypatch, metric, n, d, k, nq):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_tensor_core_path_is_exact(lib, orc, monkeypatch, metric, n, d, k, nq, cta_group):
     """tcgen05 GEMM candidate generation + exact re-rank (csrc/bf_tensor.cu): same bar as the scan -- ids bit-exact,
-    distances bit-identical -- because the re-rank uses the reference's summation order."""
+    distances bit-identical -- because the re-rank uses the reference's summation order.  cta_group = 2: the CTA-pair
+    form of the GEMM (tcgen05 cta_group::2; 20000 rows = an odd number of 128-row panels, so one pair has a phantom
+    panel)."""
     monkeypatch.setenv("B200HNSW_BF_PATH", "tensor")
+    monkeypatch.setenv("B200HNSW_BF_CG", str(cta_group))
     X = bind.lowrank_data(n, d, seed=51, latent=24, noise=0.2, normalize=(metric == bind.IP))
     X[n // 2] = X[n // 3]
     Q = bind.lowrank_data(nq, d, seed=52, latent=24, noise=0.2, normalize=(metric == bind.IP))
