@@ -22,8 +22,8 @@
 //             survivors = candidates with key - E <= U2 (k plus the rows inside the error band, ~1.4 k); only those
 //             get exact distances, then the k smallest (dist, label), closest first.
 //
-// Roles in the 192-thread CTA (Blackwell playbook): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
-// MMA issuer, warps 2-5 = epilogue (tcgen05.ld of their 32-lane quarter).  Pipelines: 4-stage smem ring (full/empty
+// Roles in the 320-thread CTA (Blackwell playbook): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+// MMA issuer, warps 2-9 = epilogue (tcgen05.ld of their 32-lane quarter = warp % 4, half of the columns each).  Pipelines: 4-stage smem ring (full/empty
 // mbarriers, tcgen05.commit frees a stage), 2 accumulator buffers of 256 TMEM columns (tmem_full / tmem_empty).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -41,7 +41,14 @@ constexpr int kGM = 128;       // rows per tile (UMMA M)
 constexpr int kGN = 256;       // queries per tile (UMMA N)
 constexpr int kGK = 64;        // K elements per stage (128 bytes of bf16 = one swizzle atom row)
 constexpr int kGStages = 4;
-constexpr int kGThreads = 192;
+// Epilogue warps: 8 = two per TMEM lane quarter, each taking half of the tile's 256 query columns.  With one warp per
+// quarter the epilogue of a tile (8 chunks of 32 columns per warp) took longer than the tile's MMAs and the tensor pipe
+// waited for free accumulators: measured at C4 with the epilogue switched off 9.7 ms (9.0 ms as CTA pairs), with half of
+// it 9.9 ms, with all of it on four warps 12.0 ms (gpurun_out/s2_bf_epi.log).
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kEpiCols = kGN / (kEpiWarps / 4);   // query columns per epilogue warp
+constexpr int kGThreads = 64 + kEpiThreads;
 constexpr uint32_t kStageA = kGM * kGK * 2;   // 16 KB
 constexpr uint32_t kStageB = kGN * kGK * 2;   // 32 KB
 constexpr uint32_t kStageBytes = kStageA + kStageB;
@@ -52,9 +59,9 @@ constexpr uint32_t kStageBytes = kStageA + kStageB;
 constexpr int kGStages2 = 6;
 constexpr uint32_t kStageB2 = (kGN / 2) * kGK * 2;   // 16 KB
 constexpr uint32_t kStageBytes2 = kStageA + kStageB2;
-constexpr int kQCap = 512;     // entries of one epilogue warp's hit queue (pass 2)
+constexpr int kQCap = 256;     // entries of one epilogue warp's hit queue (pass 2)
 constexpr uint32_t kGemmSmem = kGStages * kStageBytes + 1024 /*align*/ + 8192 /*barriers + per-tile tables*/ +
-                               4 * 2 * kQCap * 4 /*hit queues*/;
+                               kEpiWarps * 2 * kQCap * 4 /*hit queues*/;
 static_assert(kGStages2 * kStageBytes2 == kGStages * kStageBytes, "both variants share one shared-memory carve-up");
 constexpr float kErrC = 0.0078125f + 0.000244140625f;   // 2^-7 + 2^-12
 constexpr float kErrDelta = 4e-6f;
@@ -72,6 +79,7 @@ struct GemmArgs {
     uint32_t *cand_cnt;     // [nq]
     uint32_t n, nq, nq_pad, kchunks, panels, stride, qtiles, cap;
     const uint8_t *mask;    // [n] row filter of the call (bruteforce.h:114,121) or null
+    uint32_t dbg_chunks;    // chunks of 32 columns every epilogue warp evaluates (kEpiCols / 32; fewer: timing experiments)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         // the epilogue warps of both CTAs release the accumulators there); `empty` / `tfull` exist in both and receive
         // the leader's multicast commits
         for (int s = 0; s < kNS; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4 * CG); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, kEpiWarps * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {  // TMEM: all 512 columns (two 256-column accumulators)
@@ -270,7 +278,9 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         // only chunks that contain a hit (rare) walk their set bits.  Tables of the next item are prefetched into
         // registers while this one is processed and live double-buffered in shared memory.
         const int quarter = warp & 3;
-        const int et = threadIdx.x - 64;  // 0..127
+        const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
+        const int c_first = ((warp - 2) >> 2) * (kEpiCols / 32);  // this warp's chunks of 32 columns
+        constexpr int kTabPer = kGN / kEpiThreads;  // table entries staged per thread
         float *s_B = (float *)(tail + 256);          // [2][kGN]
         float *s_T = s_B + 2 * kGN;                  // [2][kGN]
         uint32_t *s_min = (uint32_t *)(s_T + 2 * kGN);  // [2][kGN] (pass 1)
@@ -282,20 +292,21 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
         bool pend = false;
         constexpr float alpha = METRIC == 1 ? -1.f : -2.f;
         uint32_t buf = 0, bphase = 0, tb = 0;
-        float pB[2], pT[2];
+        float pB[kTabPer], pT[kTabPer];
         uint32_t it = it0;
         const uint32_t tempty_leader = CG == 2 ? map_to_cta(tempty, 0) : 0u;  // tempty[b] at + 8 * b
         if (it < items) {
             const uint32_t t = it % a.qtiles;
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const uint32_t q = t * kGN + et + e * 128;
-                s_B[et + e * 128] = a.tabB[q];
-                s_T[et + e * 128] = a.tabT[q];
+            for (int e = 0; e < kTabPer; e++) {
+                const uint32_t q = t * kGN + et + e * kEpiThreads;
+                s_B[et + e * kEpiThreads] = a.tabB[q];
+                s_T[et + e * kEpiThreads] = a.tabT[q];
             }
         }
-        s_min[et] = s_min[et + 128] = s_min[kGN + et] = s_min[kGN + et + 128] = 0xFFFFFFFFu;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < kTabPer; e++) s_min[et + e * kEpiThreads] = s_min[kGN + et + e * kEpiThreads] = 0xFFFFFFFFu;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         uint32_t prev_pi = 0, prev_t = 0;
         bool have_prev = false;
         for (; it < items; it += it_step) {
@@ -304,16 +315,16 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             if (nit < items) {  // prefetch the next item's tables
                 const uint32_t nt = nit % a.qtiles;
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const uint32_t q = nt * kGN + et + e * 128;
+                for (int e = 0; e < kTabPer; e++) {
+                    const uint32_t q = nt * kGN + et + e * kEpiThreads;
                     pB[e] = a.tabB[q];
                     pT[e] = a.tabT[q];
                 }
             }
             if (MODE == 0 && have_prev) {  // flush the previous item's column minima (other table buffer)
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const int j = et + e * 128;
+                for (int e = 0; e < kTabPer; e++) {
+                    const int j = et + e * kEpiThreads;
                     if (prev_pi < sampled) a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
                     s_min[(tb ^ 1) * kGN + j] = 0xFFFFFFFFu;
                 }
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             mbar_wait(tfull + buf, bphase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < kGN / 32; c++) {
+            for (int c = c_first; c < c_first + (int)a.dbg_chunks; c++) {
                 uint32_t v[32];
                 tc_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kGN + c * 32, v);
                 float Bc[32], Tc[32];
@@ -448,19 +459,19 @@ __global__ void __launch_bounds__(kGThreads, 1) bf_gemm_kernel(const __grid_cons
             }
             if (nit < items) {
 #pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    s_B[(tb ^ 1) * kGN + et + e * 128] = pB[e];
-                    s_T[(tb ^ 1) * kGN + et + e * 128] = pT[e];
+                for (int e = 0; e < kTabPer; e++) {
+                    s_B[(tb ^ 1) * kGN + et + e * kEpiThreads] = pB[e];
+                    s_T[(tb ^ 1) * kGN + et + e * kEpiThreads] = pT[e];
                 }
             }
             prev_pi = pi; prev_t = t; have_prev = true;
             tb ^= 1;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         }
         if (MODE == 0 && have_prev && prev_pi < sampled) {
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int j = et + e * 128;
+            for (int e = 0; e < kTabPer; e++) {
+                const int j = et + e * kEpiThreads;
                 a.panelmin[(size_t)prev_pi * a.nq_pad + prev_t * kGN + j] = s_min[(tb ^ 1) * kGN + j];
             }
         }
@@ -967,6 +978,8 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     a.n = (uint32_t)n; a.nq = (uint32_t)nq; a.nq_pad = (uint32_t)nq_pad; a.kchunks = (uint32_t)(kp / kGK);
     a.panels = (uint32_t)panels; a.qtiles = (uint32_t)(nq_pad / kGN); a.cap = (uint32_t)cap_c;
     a.mask = cur_mask;
+    a.dbg_chunks = kEpiCols / 32;
+    if (const char *e = getenv("B200HNSW_BF_DEBUG_CHUNKS")) a.dbg_chunks = (uint32_t)std::min(kEpiCols / 32, std::max(0, atoi(e)));  // WRONG RESULTS: timing only
     static bool configured[16] = {};
     if (device < 16 && !configured[device]) {
         B200_CUDA_OK(cudaFuncSetAttribute(bf_gemm_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
