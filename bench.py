@@ -572,7 +572,7 @@ def run_b200(a, rank, local_rank, world):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    submit_ms = None
+    submit_ms = call_ms = None
     if pipe is not None:
         # N > 1: batch i's all_gather + merge overlaps batch i+1's search kernel (side stream, event-ordered);
         # the timed region ends only after the last exchange has finished.
@@ -581,11 +581,15 @@ def run_b200(a, rank, local_rank, world):
         inflight = int(os.environ.get("B200HNSW_BENCH_INFLIGHT", "2"))
         evs = []
         t_submit = time.perf_counter()
+        t_calls = 0.0
         for s in range(a.steps):
             if inflight > 0 and s >= inflight:
                 evs[s - inflight].synchronize()
+            t_c = time.perf_counter()
             evs.append(pipe.submit(dbatches[s % len(dbatches)].data_ptr(), ef)[2])
+            t_calls += time.perf_counter() - t_c
         submit_ms = 1e3 * (time.perf_counter() - t_submit) / a.steps
+        call_ms = 1e3 * t_calls / a.steps
         pipe.drain()
     else:
         for s in range(a.steps):
@@ -614,11 +618,14 @@ def run_b200(a, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
         # per-rank diagnostics: search-kernel ms and host submit ms per step (explains step time vs kernel time)
-        mine = torch.tensor([kernel_ms, submit_ms or 0.0], device=dev, dtype=torch.float64)
-        allr = torch.empty((world, 2), device=dev, dtype=torch.float64)
+        mine = torch.tensor([kernel_ms, submit_ms or 0.0, call_ms or 0.0], device=dev, dtype=torch.float64)
+        allr = torch.empty((world, 3), device=dev, dtype=torch.float64)
         dist.all_gather_into_tensor(allr, mine)
+        # host_submit_ms: host loop per step incl. its wait for the batch `inflight` steps back; host_call_ms: the part
+        # spent inside the submit call itself (launches, copies, stream memory operations)
         rank_diag = {"kernel_ms": [round(x, 4) for x in allr[:, 0].tolist()],
-                     "host_submit_ms": [round(x, 4) for x in allr[:, 1].tolist()]}
+                     "host_submit_ms": [round(x, 4) for x in allr[:, 1].tolist()],
+                     "host_call_ms": [round(x, 4) for x in allr[:, 2].tolist()]}
 
     # ---- C2's ef sweep (32..256): device-resident QPS and recall per ef, outside the headline timed region
     ef_table = []
