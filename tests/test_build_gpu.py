@@ -112,6 +112,24 @@ def test_capacity_and_duplicate_label(lib):
     assert g2.cur_element_count == 1 and np.array_equal(g2.getDataByLabel(5), np.ones(8, np.float32))
     r = g.searchKnnBatch(gauss(1, 10, 8), 3, ef=10)
     assert (r["labels"][:, 0] == np.arange(10)).all()
+    # one call, labels repeated inside it and more rows than capacity: rows are staged in two passes (slot assignment,
+    # then the records written by several threads) -- the last vector of a repeated label wins, and a call that runs
+    # out of capacity keeps every row it accepted before the failing one
+    X = gauss(3, 70000, 8)
+    labels = np.arange(70000, dtype=np.uint64)
+    labels[1000] = 7                                       # row 1000 re-adds label 7 (staged by this very call)
+    labels[69999] = 7                                      # ... and so does the last row
+    g3 = lib.HierarchicalNSW(lib.L2Space(8), 70000, 8, 60)
+    g3.addPoints(X, labels)
+    assert g3.cur_element_count == 69998
+    assert np.array_equal(g3.getDataByLabel(7), X[69999])
+    assert np.array_equal(g3.getDataByLabel(12345), X[12345]) and np.array_equal(g3.getDataByLabel(69998), X[69998])
+    r3 = g3.searchKnnBatch(X[[5, 69999, 40000]], 1, ef=200)
+    assert r3["labels"][:, 0].tolist() == [5, 7, 40000]
+    g4 = lib.HierarchicalNSW(lib.L2Space(8), 40000, 4, 20)
+    with pytest.raises(lib.B200Error, match="exceeds the specified limit"):
+        g4.addPoints(X, np.arange(70000, dtype=np.uint64))
+    assert g4.cur_element_count == 40000 and np.array_equal(g4.getDataByLabel(39999), X[39999])
 
 
 @pytest.mark.parametrize("metric", [bind.L2, bind.IP])
