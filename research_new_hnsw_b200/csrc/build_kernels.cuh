@@ -149,48 +149,119 @@ __global__ void __launch_bounds__(kTeam) build_search_kernel(const BuildArgs p) 
     }
 }
 
+// Distances from the register-resident vector q to one or two rows, computed by ONE group of LPV lanes (same arithmetic
+// and summation order as eval_list, so both give bit-identical values).
+template <int LPV, int CPL, int METRIC>
+__device__ __forceinline__ void group_dist2(const float4 (&q)[CPL], const float4 *__restrict__ ra,
+                                            const float4 *__restrict__ rb, bool has2, uint32_t d4, int sub,
+                                            uint32_t gmask, float &sa, float &sb) {
+    float4 va[CPL], vb[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+        const uint32_t idx = sub + c * LPV;
+        va[c] = idx < d4 ? __ldg(ra + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+        const uint32_t idx = sub + c * LPV;
+        vb[c] = (has2 && idx < d4) ? __ldg(rb + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float2 pa = make_float2(0.f, 0.f), pb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < CPL; c++) {
+        const uint32_t idx = sub + c * LPV;
+        if (idx < d4) {
+            pa = acc4<METRIC>(pa, q[c], va[c]);
+            pb = acc4<METRIC>(pb, q[c], vb[c]);
+        }
+    }
+    sa = group_sum<LPV>(pa.x + pa.y, gmask);
+    sb = group_sum<LPV>(pb.x + pb.y, gmask);
+    if (METRIC == 1) { sa = 1.0f - sa; sb = 1.0f - sb; }
+}
+
 // getNeighborsByHeuristic2 (hnswalg.h:443-483) for one candidate list sorted closest-first: accept c iff every already
 // accepted r has dist(r, c) >= dist(base, c); stop at Mlimit.  Selected keys end up in sel[0..ns), their ids in ids[].
-// The candidate's vector is register-resident and the next candidate's is prefetched while the current one is
-// compared against the accepted set (whose rows are re-read through L1/L2).
+//
+// The reference's loop is sequential in the candidates; here a WINDOW of W = kTeam / LPV candidates is in flight, one
+// per lane group, with the same decisions:
+//   A. every group holds its candidate's vector in registers and checks it against the rows accepted BEFORE the window,
+//      two at a time, stopping at the first row that is closer to the candidate than the base point is (the sequential
+//      loop evaluated every accepted row for every candidate, one block barrier per candidate);
+//   B. the window is resolved in order: the first candidate that survived is accepted; the later survivors of the window
+//      are checked against it (one more row each) before the next one is looked at.  Block barriers: one per window plus
+//      one per ACCEPTED candidate (<= Mlimit per list) instead of three per candidate.
+// The rows of the next window are prefetched into L2 while the current one is resolved.
 template <int LPV, int CPL, int METRIC>
 __device__ __forceinline__ int heuristic_prune(const GraphView &g, const uint64_t *cand, int n, int Mlimit,
                                                uint64_t *sel, uint32_t *ids, float *dist, uint32_t &evals) {
+    constexpr int W = kTeam / LPV;
+    __shared__ uint32_t s_bad[W];
+    __shared__ uint32_t s_ev;
     const int tid = threadIdx.x;
     const int sub = tid % LPV, grp = tid / LPV;
+    const uint32_t gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << ((threadIdx.x & 31) / LPV * LPV));
     if (n < Mlimit) {  // hnswalg.h:446-448
         for (int j = tid; j < n; j += kTeam) { sel[j] = cand[j]; ids[j] = (uint32_t)cand[j] & kIdMask; }
         __syncthreads();
         return n;
     }
-    int ns = 0;
-    float4 v[CPL], vn[CPL];
-    // rows of the candidates kPruneAhead rounds ahead -> L2, so the register prefetch of the NEXT candidate below is an L2
-    // hit instead of a DRAM round trip per round (one thread per 128-byte line)
     const uint32_t row_bytes = g.d4 * 16, lpr = (row_bytes + kPfLine - 1) / kPfLine;
-    for (uint32_t i = tid; i < (uint32_t)min(n, kPruneAhead) * lpr; i += kTeam)
-        prefetch_l2((const char *)(g.vec + (size_t)((uint32_t)cand[i / lpr] & kIdMask) * g.d4) + (i % lpr) * kPfLine);
-    load_row<LPV, CPL>(v, g.vec + (size_t)((uint32_t)cand[0] & kIdMask) * g.d4, g.d4, sub);
-    for (int ci = 0; ci < n && ns < Mlimit; ci++) {
-        const uint64_t key = cand[ci];
+    auto prefetch_window = [&](int first) {
+        const int cnt = min(W, n - first);
+        for (uint32_t i = tid; i < (uint32_t)max(cnt, 0) * lpr; i += kTeam)
+            prefetch_l2((const char *)(g.vec + (size_t)((uint32_t)cand[first + i / lpr] & kIdMask) * g.d4) + (i % lpr) * kPfLine);
+    };
+    prefetch_window(0);
+    if (tid == 0) s_ev = 0;  // (ordered before its use by the barriers of the first window)
+    int ns = 0;
+    uint32_t my_evals = 0;
+    for (int base = 0; base < n && ns < Mlimit; base += W) {
+        const int wcount = min(W, n - base);
+        const bool has = grp < wcount;
+        const uint64_t key = has ? cand[base + grp] : 0;
         const float dq = ord2f((uint32_t)(key >> 32));
-        if (ci + kPruneAhead < n && (uint32_t)tid < lpr)
-            prefetch_l2((const char *)(g.vec + (size_t)((uint32_t)cand[ci + kPruneAhead] & kIdMask) * g.d4) + tid * kPfLine);
-        if (ci + 1 < n) load_row<LPV, CPL>(vn, g.vec + (size_t)((uint32_t)cand[ci + 1] & kIdMask) * g.d4, g.d4, sub);
-        eval_list<kTeam, LPV, CPL, METRIC, true>(v, g.vec, g.d4, ids, ns, dist, grp, sub);
-        evals += ns;
-        __syncthreads();
-        bool bad = false;
-        for (int j = tid; j < ns; j += kTeam) bad |= dist[j] < dq;
-        bad = __syncthreads_or(bad);
-        if (!bad) {
-            if (tid == 0) { sel[ns] = key; ids[ns] = (uint32_t)key & kIdMask; }
-            ns++;
+        float4 v[CPL];
+        if (has) load_row<LPV, CPL>(v, g.vec + (size_t)((uint32_t)key & kIdMask) * g.d4, g.d4, sub);
+        prefetch_window(base + W);
+        // ---- A: against the rows accepted before this window ----
+        bool bad = !has;
+        for (int r = 0; r < ns && !bad; r += 2) {
+            const bool two = r + 1 < ns;
+            float da, db;
+            group_dist2<LPV, CPL, METRIC>(v, g.vec + (size_t)ids[r] * g.d4, g.vec + (size_t)ids[two ? r + 1 : r] * g.d4, two,
+                                          g.d4, sub, gmask, da, db);
+            my_evals += two ? 2u : 1u;
+            bad = da < dq || (two && db < dq);
         }
+        if (sub == 0) s_bad[grp] = bad ? 1u : 0u;
         __syncthreads();
-#pragma unroll
-        for (int cc = 0; cc < CPL; cc++) v[cc] = vn[cc];
+        // ---- B: resolve the window in candidate order ----
+        for (int w = 0; w < wcount && ns < Mlimit; w++) {
+            if (s_bad[w]) continue;  // (uniform: every thread reads the same word)
+            const uint64_t kw = cand[base + w];
+            const uint32_t idw = (uint32_t)kw & kIdMask;
+            if (tid == 0) { sel[ns] = kw; ids[ns] = idw; }
+            ns++;
+            if (w + 1 < wcount && ns < Mlimit) {
+                if (has && grp > w && !bad) {
+                    float da, db;
+                    group_dist2<LPV, CPL, METRIC>(v, g.vec + (size_t)idw * g.d4, g.vec + (size_t)idw * g.d4, false, g.d4, sub,
+                                                  gmask, da, db);
+                    my_evals += 1u;
+                    if (da < dq) {
+                        bad = true;
+                        if (sub == 0) s_bad[grp] = 1u;
+                    }
+                }
+                __syncthreads();  // the later survivors' verdicts before the next candidate of the window is looked at
+            }
+        }
+        __syncthreads();  // ids[] / sel[] of this window are visible, s_bad[] may be rewritten
     }
+    if (sub == 0 && my_evals) atomicAdd(&s_ev, my_evals);  // one count per group
+    __syncthreads();
+    evals += s_ev;
     return ns;
 }
 
