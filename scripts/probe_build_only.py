@@ -13,6 +13,13 @@ for rep in range(2):
     print("%s rep %d: %.2f s (%.0f pts/s), addPoints %.2f s, flush events %.0f ms, D/pt %.1f, dropped reverse edges %d" % (
         os.path.basename(os.environ.get("B200HNSW_LIB", "head")), rep, sec, len(X) / sec, t_add, st["last_kernel_ms"],
         st["dist_evals"] / len(X), st["dropped_reverse_edges"]), flush=True)
+    if rep == 1 and os.environ.get("PROBE_RECALL"):
+        # recall@10 of the GPU-built graph at the bench's ef (reference-built graph: 0.950-0.952, same queries)
+        Qr = lowrank_data(10000, 128, seed=2)
+        bf = pkg.BruteforceSearch(pkg.L2Space(128), len(X)); bf.addPoints(X); gt = bf.searchKnnBatch(Qr, 10)["labels"]; del bf
+        for ef in (28, 64):
+            lab = g.searchKnnBatch(Qr, 10, ef=ef)["labels"]
+            print("recall@10 of the built graph at ef=%d: %.4f" % (ef, np.mean([len(set(a) & set(b)) for a, b in zip(lab.tolist(), gt.tolist())]) / 10), flush=True)
     if rep == 1 and os.environ.get("PROBE_SEARCH_AFTER"):
         # the same amount of traversal as one full build batch, through the search kernel (for comparison)
         Qb = X[-16384:]
