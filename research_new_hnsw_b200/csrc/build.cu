@@ -433,33 +433,7 @@ int HnswIndex::flush_locked() {
     auto since = [&](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
-    // ---- upload vectors + labels of the staged points (records carry empty lists) ----
-    {
-        const size_t chunk = std::max<size_t>(1, std::min<size_t>(n_new, (size_t)(256u << 20) / rec));
-        uint32_t *raw = nullptr;
-        B200_CUDA_OK(cudaMalloc(&raw, chunk * rec));
-        for (size_t first = linked; first < m.cur; first += chunk) {
-            const size_t cnt = std::min(chunk, m.cur - first);
-            cudaError_t e = cudaMemcpy(raw, m.level0 + first * rec, cnt * rec, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) {
-                deinterleave_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256>>>(
-                    raw, rec / 4, (uint32_t)first, (uint32_t)cnt, (uint32_t)m.maxM0, (uint32_t)m.dim, (uint32_t)dev.d4,
-                    (uint32_t)m.cur, (float *)dev.vec, dev.links0, dev.labels, dev.err_flag);
-                e = cudaDeviceSynchronize();
-            }
-            if (e != cudaSuccess) {
-                cudaFree(raw);
-                set_error(std::string("CUDA error during upload: ") + cudaGetErrorString(e));
-                return B200HNSW_E_CUDA;
-            }
-        }
-        cudaFree(raw);
-    }
-    {
-        int rc16 = sync_bf16(linked, n_new);
-        if (rc16) return rc16;
-    }
-    const double ms_upload = since(t_start);
+    // (the rows themselves are uploaded further down, chunk by chunk, while the first batches are already being linked)
     // ---- upper-level list slots of the staged points (appended after the existing ones) ----
     {
         std::vector<uint32_t> base(n_new, kEmpty);
@@ -548,36 +522,90 @@ int HnswIndex::flush_locked() {
     B200_CUDA_OK(cudaMemcpyAsync(d_lp, lp_all.data(), lp_all.size() * 4, cudaMemcpyHostToDevice, stream));
     B200_CUDA_OK(cudaMemcpyAsync(d_ll, ll_all.data(), ll_all.size() * 4, cudaMemcpyHostToDevice, stream));
 
-    const double ms_plan = since(t_start) - ms_upload;
+    const double ms_plan = since(t_start);
     cudaEvent_t e0, e1;
     B200_CUDA_OK(cudaEventCreate(&e0));
     B200_CUDA_OK(cudaEventCreate(&e1));
-    B200_CUDA_OK(cudaEventRecord(e0, stream));
     uint64_t launches = 0;
     int rc = 0;
+    // ---- rows + labels of the staged points (records carry empty lists), overlapped with the build ----
+    // The records go up in 32 MB chunks on their own stream (two staging buffers; a pageable source makes every copy
+    // block the host until it is staged, which is the time the chunks are cut for); the build stream waits for the event
+    // of the chunk that completes a batch's rows, so the first batches are linked while the later rows are still on
+    // their way -- a million 128-d rows are ~0.1 s of H2D that used to precede the first kernel.
+    struct UploadScratch {
+        uint32_t *raw[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaStream_t up = nullptr;
+        ~UploadScratch() {
+            for (int b = 0; b < 2; b++) { cudaFree(raw[b]); if (ev[b]) cudaEventDestroy(ev[b]); }
+            if (up) cudaStreamDestroy(up);
+        }
+    } us;
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(n_new, env_size("B200HNSW_UPLOAD_CHUNK", (size_t)32 << 20) / rec + 1));
+    B200_CUDA_OK(cudaStreamCreateWithFlags(&us.up, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        B200_CUDA_OK(cudaMalloc(&us.raw[b], chunk * rec));
+        B200_CUDA_OK(cudaEventCreateWithFlags(&us.ev[b], cudaEventDisableTiming));
+    }
+    double ms_upload = 0.0;
+    size_t uploaded = linked0;  // rows [0, uploaded) are on the device (or on their way, ordered before the build stream)
+    size_t n_chunks = 0;
+    auto upload_next = [&]() -> int {
+        const auto t_u = std::chrono::steady_clock::now();
+        const size_t cnt = std::min(chunk, m.cur - uploaded);
+        const int b = (int)(n_chunks & 1);
+        if (n_chunks >= 2) B200_CUDA_OK(cudaEventSynchronize(us.ev[b]));  // the kernel that last read this buffer is done
+        B200_CUDA_OK(cudaMemcpyAsync(us.raw[b], m.level0 + uploaded * rec, cnt * rec, cudaMemcpyHostToDevice, us.up));
+        deinterleave_kernel<<<(unsigned)((cnt * 32 + 255) / 256), 256, 0, us.up>>>(
+            us.raw[b], rec / 4, (uint32_t)uploaded, (uint32_t)cnt, (uint32_t)m.maxM0, (uint32_t)m.dim, (uint32_t)dev.d4,
+            (uint32_t)m.cur, (float *)dev.vec, dev.links0, dev.labels, dev.err_flag);
+        B200_CUDA_OK(cudaGetLastError());
+        {
+            const int rc16 = sync_bf16(uploaded, cnt, us.up);
+            if (rc16) return rc16;
+        }
+        B200_CUDA_OK(cudaEventRecord(us.ev[b], us.up));
+        B200_CUDA_OK(cudaStreamWaitEvent(stream, us.ev[b], 0));
+        if (n_chunks == 0) B200_CUDA_OK(cudaEventRecord(e0, stream));  // kernel time is counted from the first rows on
+        uploaded += cnt;
+        n_chunks++;
+        ms_upload += since(t_u);
+        return 0;
+    };
     if (linked == 0) {
         dev_entry = 0;
         dev_maxlevel = m.levels[0];
         linked = 1;
     }
-    for (const BatchPlan &bp : plan) {
-        a.first = bp.first; a.batch = bp.batch; a.lists = bp.lists;
-        a.entry = bp.entry; a.maxlevel = bp.maxlevel;
-        a.list_off = d_off + (bp.first - linked0);
-        a.list_point = d_lp + bp.lists_off;
-        a.list_level = d_ll + bp.lists_off;
-        rc = nb ? build_run_batch_insert_nb(prm.metric, a, smem_search, smem_link, stream)
-                : build_run_batch_insert(prm.metric, a, smem_search, smem_link, stream);
-        if (rc) break;
-        launches += 3;
-        const size_t last = (size_t)bp.first + bp.batch - 1;
-        if (m.levels[last] > dev_maxlevel) {
-            dev_entry = (uint32_t)last;
-            dev_maxlevel = m.levels[last];
+    size_t next_batch = 0;
+    while (rc == 0 && (uploaded < m.cur || next_batch < plan.size())) {
+        if (uploaded < m.cur) {
+            rc = upload_next();
+            if (rc) break;
         }
-        linked = (size_t)bp.first + bp.batch;
+        // every batch whose rows are complete
+        while (next_batch < plan.size() && (size_t)plan[next_batch].first + plan[next_batch].batch <= uploaded) {
+            const BatchPlan &bp = plan[next_batch++];
+            a.first = bp.first; a.batch = bp.batch; a.lists = bp.lists;
+            a.entry = bp.entry; a.maxlevel = bp.maxlevel;
+            a.list_off = d_off + (bp.first - linked0);
+            a.list_point = d_lp + bp.lists_off;
+            a.list_level = d_ll + bp.lists_off;
+            rc = nb ? build_run_batch_insert_nb(prm.metric, a, smem_search, smem_link, stream)
+                    : build_run_batch_insert(prm.metric, a, smem_search, smem_link, stream);
+            if (rc) break;
+            launches += 3;
+            const size_t last = (size_t)bp.first + bp.batch - 1;
+            if (m.levels[last] > dev_maxlevel) {
+                dev_entry = (uint32_t)last;
+                dev_maxlevel = m.levels[last];
+            }
+            linked = (size_t)bp.first + bp.batch;
+        }
     }
     if (rc == 0) {
+        if (n_chunks == 0) B200_CUDA_OK(cudaEventRecord(e0, stream));
         B200_CUDA_OK(cudaEventRecord(e1, stream));
         B200_CUDA_OK(cudaStreamSynchronize(stream));
         if (BuildProfile *prof = build_profile()) {

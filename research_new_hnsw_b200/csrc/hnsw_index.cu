@@ -125,14 +125,15 @@ int HnswIndex::alloc_device(size_t cap) {
 }
 
 // refresh the bf16 copy of rows [first, first+count) from the fp32 rows already in HBM
-int HnswIndex::sync_bf16(size_t first, size_t count) {
+// bf16 copy of rows [first, first + count) (storage variant).  With a stream: enqueued there, no synchronisation.
+int HnswIndex::sync_bf16(size_t first, size_t count, cudaStream_t st) {
     if (prm.storage != B200HNSW_BF16 || !count) return 0;
     B200_CUDA_OK(cudaSetDevice(dev.device));
     const size_t tot = count * dev.d16;
-    rows_to_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(dev.vec, (uint32_t)dev.d4, (uint32_t)dev.d16, (uint32_t)first,
-                                                              (uint32_t)count, dev.vec16);
+    rows_to_bf16_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(dev.vec, (uint32_t)dev.d4, (uint32_t)dev.d16,
+                                                                     (uint32_t)first, (uint32_t)count, dev.vec16);
     B200_CUDA_OK(cudaGetLastError());
-    B200_CUDA_OK(cudaDeviceSynchronize());
+    if (!st) B200_CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
 

@@ -107,7 +107,7 @@ struct HnswIndex {
     bool revived_on_device = false;
     uint64_t flags_on_device_hash = 0;   // content hash of dev.flags as last uploaded
     bool flags_on_device_valid = false;  // false after anything else wrote dev.flags (scatter_rows_kernel) or reallocated it
-    int sync_bf16(size_t first, size_t count);
+    int sync_bf16(size_t first, size_t count, cudaStream_t st = nullptr);
     // kernel launch only; the caller holds `rw` (shared is enough unless `allowed` is given or the marks are dirty)
     int launch_search(const float *dQ_, size_t nq, size_t k, size_t ef_, uint64_t *dl, float *dd, uint32_t *dc,
                       uint32_t *dw, cudaStream_t st, const uint8_t *allowed = nullptr);
