@@ -514,10 +514,20 @@ int HnswIndex::flush_locked() {
             lk += used;
         }
     }
-    uint32_t *d_off = nullptr, *d_lp = nullptr, *d_ll = nullptr;
-    B200_CUDA_OK(cudaMalloc(&d_off, std::max<size_t>(n_new, 1) * 4));
-    B200_CUDA_OK(cudaMalloc(&d_lp, std::max<size_t>(lp_all.size(), 1) * 4));
-    B200_CUDA_OK(cudaMalloc(&d_ll, std::max<size_t>(ll_all.size(), 1) * 4));
+    if (bld.plan_off_cap < n_new) {
+        cudaFree(bld.plan_off);
+        bld.plan_off = nullptr; bld.plan_off_cap = 0;
+        B200_CUDA_OK(cudaMalloc(&bld.plan_off, std::max<size_t>(n_new, 1) * 4));
+        bld.plan_off_cap = std::max<size_t>(n_new, 1);
+    }
+    if (bld.plan_lists_cap < lp_all.size()) {
+        cudaFree(bld.plan_lp); cudaFree(bld.plan_ll);
+        bld.plan_lp = bld.plan_ll = nullptr; bld.plan_lists_cap = 0;
+        B200_CUDA_OK(cudaMalloc(&bld.plan_lp, std::max<size_t>(lp_all.size(), 1) * 4));
+        B200_CUDA_OK(cudaMalloc(&bld.plan_ll, std::max<size_t>(lp_all.size(), 1) * 4));
+        bld.plan_lists_cap = std::max<size_t>(lp_all.size(), 1);
+    }
+    uint32_t *d_off = bld.plan_off, *d_lp = bld.plan_lp, *d_ll = bld.plan_ll;
     B200_CUDA_OK(cudaMemcpyAsync(d_off, off_all.data(), n_new * 4, cudaMemcpyHostToDevice, stream));
     B200_CUDA_OK(cudaMemcpyAsync(d_lp, lp_all.data(), lp_all.size() * 4, cudaMemcpyHostToDevice, stream));
     B200_CUDA_OK(cudaMemcpyAsync(d_ll, ll_all.data(), ll_all.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -533,21 +543,20 @@ int HnswIndex::flush_locked() {
     // block the host until it is staged, which is the time the chunks are cut for); the build stream waits for the event
     // of the chunk that completes a batch's rows, so the first batches are linked while the later rows are still on
     // their way -- a million 128-d rows are ~0.1 s of H2D that used to precede the first kernel.
-    struct UploadScratch {
-        uint32_t *raw[2] = {nullptr, nullptr};
-        cudaEvent_t ev[2] = {nullptr, nullptr};
-        cudaStream_t up = nullptr;
-        ~UploadScratch() {
-            for (int b = 0; b < 2; b++) { cudaFree(raw[b]); if (ev[b]) cudaEventDestroy(ev[b]); }
-            if (up) cudaStreamDestroy(up);
-        }
-    } us;
+    struct { uint32_t *raw[2]; cudaEvent_t ev[2]; cudaStream_t up; } us;
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(n_new, env_size("B200HNSW_UPLOAD_CHUNK", (size_t)32 << 20) / rec + 1));
-    B200_CUDA_OK(cudaStreamCreateWithFlags(&us.up, cudaStreamNonBlocking));
-    for (int b = 0; b < 2; b++) {
-        B200_CUDA_OK(cudaMalloc(&us.raw[b], chunk * rec));
-        B200_CUDA_OK(cudaEventCreateWithFlags(&us.ev[b], cudaEventDisableTiming));
+    if (!bld.up_stream) {
+        B200_CUDA_OK(cudaStreamCreateWithFlags(&bld.up_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) B200_CUDA_OK(cudaEventCreateWithFlags(&bld.up_ev[b], cudaEventDisableTiming));
     }
+    if (bld.up_raw_bytes < chunk * rec) {
+        for (int b = 0; b < 2; b++) { cudaFree(bld.up_raw[b]); bld.up_raw[b] = nullptr; }
+        bld.up_raw_bytes = 0;
+        for (int b = 0; b < 2; b++) B200_CUDA_OK(cudaMalloc(&bld.up_raw[b], chunk * rec));
+        bld.up_raw_bytes = chunk * rec;
+    }
+    for (int b = 0; b < 2; b++) { us.raw[b] = bld.up_raw[b]; us.ev[b] = bld.up_ev[b]; }
+    us.up = bld.up_stream;
     double ms_upload = 0.0;
     size_t uploaded = linked0;  // rows [0, uploaded) are on the device (or on their way, ordered before the build stream)
     size_t n_chunks = 0;
@@ -649,7 +658,7 @@ int HnswIndex::flush_locked() {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc) cudaStreamSynchronize(stream);
-    cudaFree(d_off); cudaFree(d_lp); cudaFree(d_ll);
+    if (build_profile()) fprintf(stderr, "[b200hnsw build profile] flush total %.1f ms\n", since(t_start));
     dev.n = linked;
     mirror_dirty = true;
     flags_dirty = true;
@@ -660,7 +669,9 @@ void BuildScratch::release() {
     cudaFree(plevel); cudaFree(cand); cudaFree(cand_cnt); cudaFree(list_off); cudaFree(list_point);
     cudaFree(list_level); cudaFree(incnt); cudaFree(incoming); cudaFree(aff_node); cudaFree(aff_level);
     cudaFree(aff_count); cudaFree(work); cudaFree(batch_ids); cudaFree(newlists); cudaFree(stage_rows);
-    cudaFree(stage_labels);
+    cudaFree(stage_labels); cudaFree(plan_off); cudaFree(plan_lp); cudaFree(plan_ll);
+    for (int b = 0; b < 2; b++) { cudaFree(up_raw[b]); if (up_ev[b]) cudaEventDestroy(up_ev[b]); }
+    if (up_stream) cudaStreamDestroy(up_stream);
     *this = BuildScratch();
 }
 

@@ -30,6 +30,14 @@ struct BuildScratch {
     float *stage_rows = nullptr;
     uint64_t *stage_labels = nullptr;
     size_t stage_cap = 0;
+    // flush(): batch plan on the device and the upload pipeline, kept between calls (a cudaFree at the end of every
+    // flush synchronises the device and was seen to take up to 0.8 s)
+    uint32_t *plan_off = nullptr, *plan_lp = nullptr, *plan_ll = nullptr;
+    size_t plan_off_cap = 0, plan_lists_cap = 0;
+    uint32_t *up_raw[2] = {nullptr, nullptr};
+    size_t up_raw_bytes = 0;
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};
+    cudaStream_t up_stream = nullptr;
     void release();
 };
 

@@ -7,8 +7,9 @@ import research_new_hnsw_b200 as pkg
 from research_new_hnsw_b200.synth import lowrank_data
 X = lowrank_data(1_000_000, 128, seed=1)
 for rep in range(2):
-    g = pkg.HierarchicalNSW(pkg.L2Space(128), len(X), 32, 200)
+    t_c = time.time(); g = pkg.HierarchicalNSW(pkg.L2Space(128), len(X), 32, 200); t_c = time.time() - t_c
     t = time.time(); g.addPoints(X); t_add = time.time() - t; g.flush(); sec = time.time() - t
+    print("constructor %.3f s" % t_c, flush=True)
     st = g.stats()
     print("%s rep %d: %.2f s (%.0f pts/s), addPoints %.2f s, flush events %.0f ms, D/pt %.1f, dropped reverse edges %d" % (
         os.path.basename(os.environ.get("B200HNSW_LIB", "head")), rep, sec, len(X) / sec, t_add, st["last_kernel_ms"],
