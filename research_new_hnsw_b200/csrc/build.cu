@@ -657,7 +657,10 @@ int HnswIndex::flush_locked() {
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    if (rc) cudaStreamSynchronize(stream);
+    if (rc) {  // nothing of this flush may still be running when the buffers are reused
+        cudaStreamSynchronize(stream);
+        cudaStreamSynchronize(bld.up_stream);
+    }
     if (build_profile()) fprintf(stderr, "[b200hnsw build profile] flush total %.1f ms\n", since(t_start));
     dev.n = linked;
     mirror_dirty = true;
