@@ -332,3 +332,27 @@ def test_replace_deleted_churn_keeps_recall(lib, orc):
     rec_f = _recall(fresh.searchKnnBatch(Q, 10, ef=64)["labels"], gt)
     assert rec_g >= rec_c - 0.015 and rec_g >= rec_f - 0.015, (rec_g, rec_c, rec_f)
     _check_graph(g, n, M)
+
+
+def test_build_with_bf16_storage(lib):
+    """addPoints on an index with the bf16 storage variant: the bf16 copy of the rows is produced chunk by chunk on the
+    upload stream of flush() (csrc/build.cu); the graph is built from the fp32 rows, so it is the SAME graph as the fp32
+    index's and the bf16 traversal + fp32 re-rank must find (almost) the same neighbours."""
+    n, d = 50_000, 64
+    X = bind.lowrank_data(n, d, seed=21, latent=12, noise=0.15)
+    Q = bind.lowrank_data(500, d, seed=22, latent=12, noise=0.15)
+    a = lib.HierarchicalNSW(lib.L2Space(d), n, 16, 100)
+    b = lib.HierarchicalNSW(lib.L2Space(d), n, 16, 100, storage=1)
+    for g in (a, b):
+        g.addPoints(X[:30_000])
+        g.flush()
+        g.addPoints(X[30_000:])                       # second flush: chunked upload behind an existing graph
+    ra = a.searchKnnBatch(Q, 10, ef=64)
+    rb = b.searchKnnBatch(Q, 10, ef=64)
+    for i in (0, 777, 31_234, n - 1):
+        assert np.array_equal(a.get_linklist_at_level(i, 0), b.get_linklist_at_level(i, 0))
+    same = np.mean([len(set(x) & set(y)) for x, y in zip(ra["labels"].tolist(), rb["labels"].tolist())]) / 10
+    assert same >= 0.98, same
+    ok = ra["labels"] == rb["labels"]
+    assert np.allclose(ra["dists"][ok], rb["dists"][ok], rtol=1e-5, atol=1e-6)   # fp32 distances after the re-rank
+
