@@ -11,7 +11,7 @@ from research_new_hnsw_b200 import capi
 from research_new_hnsw_b200.synth import lowrank_data
 n, d, nq, k, ef, W = int(os.environ.get("N", 1000000)), 128, 10000, 10, int(os.environ.get("EF", 16)), 8
 X = lowrank_data(n, d, seed=1); Q = [torch.from_numpy(lowrank_data(nq, d, seed=2 + i)).cuda() for i in range(2)]
-g = pkg.HierarchicalNSW(pkg.L2Space(d), n, 32, 200); g.addPoints(X); g.flush()
+g = pkg.HierarchicalNSW(pkg.L2Space(d), n, 32, 200, storage=1 if os.environ.get("BF16") else 0); g.addPoints(X); g.flush()
 block = nq * k * 12
 area = torch.zeros(W * block, dtype=torch.uint8, device="cuda")
 peers = torch.zeros(W * block, dtype=torch.uint8, device="cuda")
