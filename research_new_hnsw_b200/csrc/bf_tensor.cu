@@ -595,21 +595,24 @@ constexpr int kRrLane = 36;
 constexpr int kRrStride = 4 * kRrLane;  // floats per staged row
 
 template <int METRIC>
-__global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
+__global__ void __launch_bounds__(kRrThreads, 4) bf_rerank_kernel(const float4 *__restrict__ X, const uint64_t *__restrict__ labels,
                                                               const float *__restrict__ xn2, const float *__restrict__ qn2,
                                                               const float *__restrict__ Q, uint32_t dim, uint32_t d4,
                                                               uint32_t lane_chunks, const uint2 *__restrict__ cand,
-                                                              const uint32_t *__restrict__ cand_cnt, uint32_t cap, uint32_t k,
-                                                              uint32_t n, uint64_t *__restrict__ out_l,
+                                                              const uint32_t *__restrict__ cand_cnt, uint32_t cap, uint32_t scap,
+                                                              uint32_t k, uint32_t n, uint64_t *__restrict__ out_l,
                                                               float *__restrict__ out_d, uint32_t *__restrict__ out_c,
                                                               uint32_t *__restrict__ overflow) {
     extern __shared__ __align__(16) unsigned char sm[];
     float *qs = (float *)sm;                              // [4][qstr] query, transposed: qs[l * qstr + c] = Q[4c + l]
     const uint32_t qstr = ((d4 + 3) & ~3u) + 4;           // (+4: the four l-rows start in different bank groups)
-    float *fd = qs + 4 * qstr;                            // [cap] exact distances of the survivors
-    uint32_t *ids = (uint32_t *)(fd + cap);               // [cap] candidate rows, later survivor rows
-    uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [cap] (key + E, key - E) per candidate, later survivor labels
-    float *tile = (float *)(cl + cap);                    // [max(kRrRows*kRrStride, cap)]
+    // Per-candidate arrays are sized by cap, per-SURVIVOR arrays by scap (<= cap; k plus the rows inside the error band
+    // are a small fraction of the candidates): 54 KB instead of 73 KB at cap 2048, i.e. four resident CTAs per SM.
+    float *fd = qs + 4 * qstr;                            // [scap] survivor staging list, then their exact distances
+    uint32_t *ids = (uint32_t *)(fd + scap);              // [cap] candidate rows, later survivor rows
+    uint64_t *cl = (uint64_t *)(ids + cap + (cap & 1));   // [scap] survivor labels
+    float *tile = (float *)(cl + scap);                   // [max(kRrRows*kRrStride, 2*cap)]: (key+E, key-E) of every
+                                                          // candidate in steps A/B, the staged rows in step C
     __shared__ uint32_t s_part[kRrThreads / 32];
     __shared__ uint32_t s_hist[kRrThreads];
     __shared__ uint32_t s_cnt;
@@ -624,7 +627,7 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
     for (uint32_t i = tid; i < d4 * 4; i += kRrThreads) qs[(i & 3) * qstr + (i >> 2)] = i < dim ? Q[(size_t)q * dim + i] : 0.f;
     // ---- A: candidates and their error bounds ----
     const float q2 = qn2[q], qn = sqrtf(q2);
-    float2 *he = (float2 *)cl;  // (key + E, key - E); cl[] proper is only written in step C
+    float2 *he = (float2 *)tile;  // (key + E, key - E); tile[] proper is only written in step C
     for (uint32_t i = tid; i < cnt; i += kRrThreads) {
         const uint2 c = cand[(size_t)q * cap + i];
         ids[i] = c.x;
@@ -687,8 +690,8 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
         prefix = 0xFFFFFFFFu;
     }
     const float u2 = ord2f(prefix);
-    // survivors, compacted in place (tile[] is reused as a staging list first)
-    uint32_t *surv = (uint32_t *)tile;
+    // survivors, compacted in place (fd[] is reused as a staging list first)
+    uint32_t *surv = (uint32_t *)fd;
     for (uint32_t b0 = 0; b0 < cnt; b0 += kRrThreads) {
         const uint32_t i = b0 + tid;
         const bool keep = i < cnt && (cnt <= k || he[i].y <= u2);
@@ -696,10 +699,15 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
         uint32_t base = 0;
         if (lane == 0 && m) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) surv[base + __popc(m & ((1u << lane) - 1u))] = ids[i];
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < scap) surv[pos] = ids[i];
     }
     __syncthreads();
-    const uint32_t ns = s_cnt;  // <= cnt <= cap words fit in tile[] (sized max(kRrRows*kRrStride, cap))
+    const uint32_t ns = s_cnt;
+    if (ns > scap) {  // more rows inside the error band than the survivor arrays hold: handled like a full candidate buffer
+        if (tid == 0) atomicAdd(overflow, 1u);
+        return;
+    }
     for (uint32_t i = tid; i < ns; i += kRrThreads) ids[i] = surv[i];
     __syncthreads();
     // ---- C: exact distances of the survivors in reference order ----
@@ -829,7 +837,7 @@ __global__ void __launch_bounds__(kRrThreads) bf_rerank_kernel(const float4 *__r
 template <int METRIC>
 static void launch_rerank(unsigned grid, size_t smem, cudaStream_t st, const float4 *X, const uint64_t *labels,
                           const float *xn2, const float *qn2, const float *Q, uint32_t dim, uint32_t d4, uint32_t lane_chunks,
-                          const uint2 *cand, const uint32_t *cand_cnt, uint32_t cap, uint32_t k, uint32_t n,
+                          const uint2 *cand, const uint32_t *cand_cnt, uint32_t cap, uint32_t scap, uint32_t k, uint32_t n,
                           uint64_t *out_l, float *out_d, uint32_t *out_c, uint32_t *overflow) {
     static bool cfg[16] = {};  // function attributes are per device
     int dv = 0;
@@ -839,7 +847,7 @@ static void launch_rerank(unsigned grid, size_t smem, cudaStream_t st, const flo
         if (dv < 16) cfg[dv] = true;
     }
     bf_rerank_kernel<METRIC><<<grid, kRrThreads, smem, st>>>(X, labels, xn2, qn2, Q, dim, d4, lane_chunks, cand, cand_cnt, cap,
-                                                            k, n, out_l, out_d, out_c, overflow);
+                                                            scap, k, n, out_l, out_d, out_c, overflow);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -1052,16 +1060,19 @@ int BruteIndex::search_tensor(const float *dQ_, size_t nq, size_t k, uint64_t *d
     else if (dim > 16) lane_floats = dim >> 4 << 4;
     else if (dim > 4) lane_floats = dim >> 2 << 2;
     else lane_floats = 0;
-    const size_t rsm = ((((size_t)d4 + 3) & ~(size_t)3) + 4) * 16 + cap_c * 4 + (cap_c + (cap_c & 1)) * 4 + cap_c * 8 +
-                       std::max<size_t>((size_t)kRrRows * kRrStride, cap_c) * 4;
+    // survivors (k + the rows inside the error band) are a small fraction of the candidates; a query with more of them
+    // than scap counts as an overflow and takes the retry / exact-scan path below
+    const size_t scap = (std::min(cap_c, std::max(cap_c / 4, 4 * k)) + 3) & ~(size_t)3;
+    const size_t rsm = ((((size_t)d4 + 3) & ~(size_t)3) + 4) * 16 + scap * 4 + (cap_c + (cap_c & 1)) * 4 + scap * 8 +
+                       std::max<size_t>((size_t)kRrRows * kRrStride, 2 * cap_c) * 4;
     if (ip)
         launch_rerank<1>((unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim, (uint32_t)d4,
-                         (uint32_t)(lane_floats / 4), (const uint2 *)tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k,
-                         (uint32_t)(cur_mask ? cur_mask_rows : n), dl, dd, dc, tz.overflow);
+                         (uint32_t)(lane_floats / 4), (const uint2 *)tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)scap,
+                         (uint32_t)k, (uint32_t)(cur_mask ? cur_mask_rows : n), dl, dd, dc, tz.overflow);
     else
         launch_rerank<0>((unsigned)nq, rsm, st, dX, dLabels, tz.xn2, tz.qn2, dQ_, (uint32_t)dim, (uint32_t)d4,
-                         (uint32_t)(lane_floats / 4), (const uint2 *)tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)k,
-                         (uint32_t)(cur_mask ? cur_mask_rows : n), dl, dd, dc, tz.overflow);
+                         (uint32_t)(lane_floats / 4), (const uint2 *)tz.cand, tz.cand_cnt, (uint32_t)cap_c, (uint32_t)scap,
+                         (uint32_t)k, (uint32_t)(cur_mask ? cur_mask_rows : n), dl, dd, dc, tz.overflow);
     mark();
     B200_CUDA_OK(cudaGetLastError());
     uint32_t ov = 0;
