@@ -287,7 +287,9 @@ uint32_t pick_hash_bits(size_t ef, size_t list_cap, int team) {
     // Throughput teams (64 / 32 threads): resident queries per SM matter more than avoiding rebuilds.  Measured on the
     // 1M x 128 graph, 10 k queries (ms per batch, default-size table vs this policy): ef=64 3.31 -> 2.79, ef=128
     // 8.82 -> 5.18, ef=256 20.3 -> 10.0, with 7-20 % more evaluations from the rebuilds.
-    if (team <= 64) want = ef <= 64 ? 2048 : 1024;
+    // (re-measured with the round-2 kernel, 1024 / 2048 / 4096 slots, ms per 10 k queries: ef=64 2.02 / 1.93 / 2.12,
+    // ef=128 4.05 / 3.98 / 4.53, ef=256 8.25 / 8.15 / 9.86 -- 2048 slots at every ef)
+    if (team <= 64) want = 2048;
     if (want < need) want = need;
     uint32_t bits = 10;
     while ((1ull << bits) < want) bits++;
