@@ -171,7 +171,8 @@ int b200hnsw_index_file_size(b200hnsw_index *h, uint64_t *bytes_out);
 int b200hnsw_get_stats(b200hnsw_index *h, b200hnsw_stats *out);
 
 /* Merge of per-shard results: in = [shards][nq][k] rows gathered from every rank (device
- * pointers), out = [nq][k] smallest (dist, label) pairs, closest first.  Enqueued on cuda_stream. */
+ * pointers), each row closest first as every search returns it (ascending distance, padding last; ties in any order);
+ * out = [nq][k] smallest (dist, label) pairs, closest first.  Enqueued on cuda_stream. */
 int b200hnsw_merge_topk_device(const uint64_t *d_labels_in, const float *d_dists_in, size_t shards, size_t nq,
                                size_t k, uint64_t *d_labels_out, float *d_dists_out, void *cuda_stream);
 

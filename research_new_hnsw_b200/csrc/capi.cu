@@ -344,7 +344,8 @@ static int merge_launch(const uint64_t *l, const float *d, size_t ls, size_t ds,
         return B200HNSW_E_ARG;
     }
     if (nq == 0) return 0;
-    B200_CUDA_OK(b200::merge_level(l, d, ls, ds, shards, shards, nq, k, ol, od, 0, 0, (cudaStream_t)cuda_stream));
+    B200_CUDA_OK(b200::merge_level(l, d, ls, ds, shards, shards, nq, k, ol, od, 0, 0, (cudaStream_t)cuda_stream,
+                                   /*sorted_rows=*/true));
     return 0;
 }
 

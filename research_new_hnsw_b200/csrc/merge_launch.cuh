@@ -12,17 +12,25 @@
 namespace b200 {
 
 // one level: groups of `group` consecutive shards -> one list per group, written at out + g*ostride
+// sorted_rows: every input row is in ascending distance order (rows returned by a search are; the per-slice lists of the
+// brute-force scans are NOT)
 inline cudaError_t merge_level(const uint64_t *l, const float *d, size_t ls, size_t ds, size_t shards, size_t group,
-                               size_t nq, size_t k, uint64_t *ol, float *od, size_t ols, size_t ods, cudaStream_t st) {
+                               size_t nq, size_t k, uint64_t *ol, float *od, size_t ols, size_t ods, cudaStream_t st,
+                               bool sorted_rows = false) {
     const size_t total = std::min(group, shards) * k;
     unsigned warps = 4;
     while (warps > 1 && warps * total * 12 > 48 * 1024) warps >>= 1;
     const dim3 grid((unsigned)((nq + warps - 1) / warps), (unsigned)((shards + group - 1) / group));
-    if (warps * total * 12 <= 48 * 1024)
-        merge_topk_smem_kernel<<<grid, warps * 32, warps * total * 12, st>>>(l, d, ls, ds, (uint32_t)shards,
-                                                                               (uint32_t)group, (uint32_t)nq,
-                                                                               (uint32_t)k, ol, od, ols, ods);
-    else
+    if (warps * total * 12 <= 48 * 1024) {
+        if (sorted_rows)
+            merge_topk_smem_kernel<true><<<grid, warps * 32, warps * total * 12, st>>>(l, d, ls, ds, (uint32_t)shards,
+                                                                                     (uint32_t)group, (uint32_t)nq,
+                                                                                     (uint32_t)k, ol, od, ols, ods);
+        else
+            merge_topk_smem_kernel<false><<<grid, warps * 32, warps * total * 12, st>>>(l, d, ls, ds, (uint32_t)shards,
+                                                                                      (uint32_t)group, (uint32_t)nq,
+                                                                                      (uint32_t)k, ol, od, ols, ods);
+    } else
         merge_topk_kernel<<<grid, warps * 32, 0, st>>>(l, d, ls, ds, (uint32_t)shards, (uint32_t)group, (uint32_t)nq,
                                                        (uint32_t)k, ol, od, ols, ods);
     return cudaGetLastError();

@@ -826,6 +826,10 @@ static __global__ void merge_topk_kernel(const uint64_t *__restrict__ labels_in,
 // shared memory with broadcast reads and an early exit once a candidate's rank reaches k.  The global-memory version
 // is latency-bound and, on a high-priority exchange stream, crowds the search kernel out of the SMs.  Dynamic shared
 // memory: warps_per_cta * group * k * 12 bytes.
+// SORTED: every shard's row is in ascending distance order (search rows are: closest first, padding last), so the
+// candidates of a shard that rank before a given one form a prefix of its row -- the scan of a shard stops at its first
+// larger distance: at most rank + shards steps per candidate instead of up to shards * k.
+template <bool SORTED>
 static __global__ void merge_topk_smem_kernel(const uint64_t *__restrict__ labels_in, const float *__restrict__ dists_in,
                                               size_t lstride, size_t dstride, uint32_t shards, uint32_t group,
                                               uint32_t nq, uint32_t k, uint64_t *__restrict__ labels_out,
@@ -854,15 +858,31 @@ static __global__ void merge_topk_smem_kernel(const uint64_t *__restrict__ label
         const float dc = sd[c];
         const uint64_t lc = sl[c];
         uint32_t rank = 0;
-        for (uint32_t o = 0; o < total; o++) {
-            const float d2 = sd[o];
-            if (d2 < dc) {
-                rank++;
-            } else if (d2 == dc) {  // ties on distance are rare: only then look at the label
-                const uint64_t l2 = sl[o];
-                rank += (l2 < lc || (l2 == lc && o < c)) ? 1u : 0u;
+        if (SORTED) {
+            for (uint32_t s0_ = 0; s0_ < total && rank < k; s0_ += k) {
+                for (uint32_t o = s0_; o < s0_ + k; o++) {
+                    const float d2 = sd[o];
+                    if (d2 < dc) {
+                        rank++;
+                    } else if (d2 == dc) {  // ties on distance are rare: only then look at the label
+                        const uint64_t l2 = sl[o];
+                        rank += (l2 < lc || (l2 == lc && o < c)) ? 1u : 0u;
+                    } else {
+                        break;  // the rest of this shard's row is farther
+                    }
+                }
             }
-            if (rank >= k) break;
+        } else {
+            for (uint32_t o = 0; o < total; o++) {
+                const float d2 = sd[o];
+                if (d2 < dc) {
+                    rank++;
+                } else if (d2 == dc) {  // ties on distance are rare: only then look at the label
+                    const uint64_t l2 = sl[o];
+                    rank += (l2 < lc || (l2 == lc && o < c)) ? 1u : 0u;
+                }
+                if (rank >= k) break;
+            }
         }
         if (rank < k) {
             labels_out[(size_t)qi * k + rank] = lc;

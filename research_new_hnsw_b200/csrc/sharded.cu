@@ -270,7 +270,7 @@ int b200hnsw_sharded_search_batch(b200hnsw_sharded *g, const float *Q, size_t nq
         B200_CUDA_OK(cudaSetDevice(g->root));
         for (size_t s = 0; s < ns; s++) B200_CUDA_OK(cudaStreamWaitEvent(g->root_stream, g->ev[s], 0));
         B200_CUDA_OK(b200::merge_level((const uint64_t *)g->blocks, (const float *)(g->blocks + nq * k * 8), bb / 8, bb / 4, ns, ns,
-                                       nq, k, g->outL, g->outD, 0, 0, g->root_stream));
+                                       nq, k, g->outL, g->outD, 0, 0, g->root_stream, /*sorted_rows=*/true));
         B200_CUDA_OK(cudaEventRecord(t1, g->root_stream));
         B200_CUDA_OK(cudaMemcpyAsync(labels_out, g->outL, nq * k * 8, cudaMemcpyDeviceToHost, g->root_stream));
         B200_CUDA_OK(cudaMemcpyAsync(dists_out, g->outD, nq * k * 4, cudaMemcpyDeviceToHost, g->root_stream));
