@@ -58,3 +58,21 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.lower(), (dirpath, f)
+
+
+def test_headers_compile_standalone(tmp_path):
+    """The boundary is a C ABI: include/b200hnsw.h is valid C99 (plain pointers and sizes, no C++ or torch types), and the
+    drop-in header directory compiles on its own as C++17 without CUDA headers."""
+    import subprocess
+    c = tmp_path / "t.c"
+    c.write_text('#include "b200hnsw.h"\nint main(void) { return (int)sizeof(b200hnsw_params) == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I" + os.path.join(ROOT, "include"), str(c)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "hnswlib/hnswlib.h"\n#include "hnswlib/stop_condition.h"\n#include "hnswlib/hnswalg.h"\n'
+                   '#include "hnswlib/bruteforce.h"\n#include "hnswlib/space_l2.h"\n#include "hnswlib/space_ip.h"\n'
+                   'int main() { hnswlib::L2Space a(8); hnswlib::InnerProductSpace b(8); (void)a; (void)b; return 0; }\n')
+    r = subprocess.run(["g++", "-std=gnu++17", "-Wall", "-fsyntax-only", "-I" + os.path.join(ROOT, "research_new_hnsw_b200"),
+                        "-I" + os.path.join(ROOT, "include"), str(cpp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
